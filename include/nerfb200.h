@@ -1,0 +1,174 @@
+/*
+ * nerfb200.h -- C ABI of the B200-native NeRF ray-march hot path.
+ *
+ * The reference (thatbrguy/nerf-tf2) has no native/FFI layer at all: its hot path is Python
+ * over stock TensorFlow kernels. The entry points below are what a ctypes binding of that
+ * path binds (INTEGRATION.md shows the reference-side stub); each one cites the reference
+ * function (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a non-zero code (a cudaError_t value, or one of
+ *     NERFB200_E*); nerfb200_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers owned by the caller (torch), fp32 row-major unless
+ *     stated; the library owns only the opaque nerfb200_ctx (packed tensor-core weights).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it.
+ *   - no exceptions cross the ABI; no torch/C++ types in any signature.
+ *   - B = rays, S = samples per ray, R = B*S network rows, row = ray*S + sample
+ *     (utils/ray_utils.py:258,398,474).
+ */
+#ifndef NERFB200_H
+#define NERFB200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define NERFB200_API __attribute__((visibility("default")))
+#else
+#define NERFB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NERFB200_ABI_VERSION 1
+
+#define NERFB200_EINVAL   10001   /* bad argument                      */
+#define NERFB200_ENOTSUP  10002   /* shape outside the supported range */
+#define NERFB200_ESTATE   10003   /* e.g. weights not packed           */
+
+/* MLP arithmetic selector (`precision` arguments) */
+#define NERFB200_FP32 0   /* fp32 FMA on CUDA cores: the exact-arithmetic check path        */
+#define NERFB200_BF16 1   /* bf16 operands, fp32 accumulate, tcgen05/TMEM fused kernel       */
+#define NERFB200_FP16 2   /* fp16 operands, fp32 accumulate, tcgen05/TMEM fused kernel       */
+
+#define NERFB200_COARSE 0
+#define NERFB200_FINE   1
+
+/* Parameters of ONE 8x256 model in Keras creation order (core/model.py:366-387):
+ * dense_0..dense_7, sigma, dense_8, dense_9, rgb; each kernel [in,out] row-major then bias. */
+#define NERFB200_PARAMS_PER_MODEL 595844
+#define NERFB200_NUM_VARS_PER_MODEL 24
+#define NERFB200_PARAMS_TOTAL (2 * NERFB200_PARAMS_PER_MODEL)  /* coarse then fine */
+
+typedef struct nerfb200_ctx nerfb200_ctx;
+
+NERFB200_API const char* nerfb200_last_error(void);
+NERFB200_API int nerfb200_abi_version(void);
+
+/* Offsets (in floats) of the 24 variables of one model inside its flat parameter block,
+ * order = model.trainable_variables (kernel, bias per layer). offsets[24] = total. */
+NERFB200_API int nerfb200_param_offsets(int64_t* offsets /* [25] */);
+
+/* ---- a1/a2: camera rays ---------------------------------------------------------------
+ * get_rays (utils/ray_utils.py:6-51; fp64 maths, cast to fp32 as base_dataset.py:849-852) and
+ * get_rays_tf (utils/ray_utils.py:53-106; fp32 maths). Ray id = row*W + col; writes rays
+ * [ray0, ray0+n_rays) to rays_o/rays_d[n_rays,3]. K = 3x3 intrinsic, c2w = 4x4, row-major
+ * HOST arrays (they are 25 scalars; passed by value to the kernel). */
+NERFB200_API int nerfb200_get_rays(int H, int W, const double* K, const double* c2w, int64_t ray0,
+                      int64_t n_rays, float* rays_o, float* rays_d, void* stream);
+NERFB200_API int nerfb200_get_rays_f32(int H, int W, const float* K, const float* c2w, int64_t ray0,
+                          int64_t n_rays, float* rays_o, float* rays_d, void* stream);
+/* Sample-mode training input (core/base_dataset.py:555-621 computes all H*W rays then gathers):
+ * rays for an explicit list of pixel ids (int32 device array), fp32 maths as get_rays_tf. */
+NERFB200_API int nerfb200_get_rays_at(int H, int W, const float* K, const float* c2w, const int32_t* pixel_ids,
+                         int64_t n_rays, float* rays_o, float* rays_d, void* stream);
+
+/* ---- a3: stratified sampler ------------------------------------------------------------
+ * create_input_batch_coarse_model (utils/ray_utils.py:137-274). near/far [B]. perturb!=0:
+ * t = left + u*width with u = u_coarse[B,Nc] if non-NULL else Philox(seed, ray0+ray, sample);
+ * perturb==0: bin mid-points (with the bin_widths fix of SURVEY.md App. B1).
+ * Outputs t_vals[B,Nc], bin_edges[B,Nc+1] (left = [:, :-1], right = [:, 1:]). */
+NERFB200_API int nerfb200_sample_coarse(int64_t B, int Nc, int lin_inv_depth, int perturb, const float* near,
+                           const float* far, const float* u_coarse, uint64_t seed, int64_t ray0,
+                           float* t_vals, float* bin_edges, void* stream);
+
+/* xyz/dir network inputs exactly as the reference materialises them (utils/ray_utils.py:251-258):
+ * xyz = o + t*d (separate multiply and add), dirs broadcast. For parity tests and the FP32
+ * path; the tensor-core kernel fuses this and never writes xyz to HBM. */
+NERFB200_API int nerfb200_make_inputs(int64_t B, int S, const float* rays_o, const float* rays_d,
+                         const float* t_vals, float* xyz /* [B*S,3] */, float* dirs /* [B*S,3] */,
+                         void* stream);
+
+/* ---- a4: positional encoding (core/model.py:289-332) -----------------------------------
+ * out[R, 3+6L]: [x, then for d in 0..2, l in 0..L-1: sin(x_d*m_l), cos(x_d*m_l)],
+ * m_l = fl32(2^l)*fl32(pi), one fp32 multiply then accurate sinf/cosf. */
+NERFB200_API int nerfb200_positional_encode(int64_t R, int L, const float* x /* [R,3] */, float* out, void* stream);
+
+/* ---- context: packed weights ------------------------------------------------------------ */
+NERFB200_API int nerfb200_create(nerfb200_ctx** out);
+NERFB200_API int nerfb200_destroy(nerfb200_ctx* ctx);
+/* (Re)pack the fp32 master parameters (flat [NERFB200_PARAMS_TOTAL], coarse then fine) into the
+ * tensor-core operand image (K-major 128B-swizzled UMMA tiles, bf16 and fp16 copies).
+ * Must be called after every optimiser step before the next forward. */
+NERFB200_API int nerfb200_pack_weights(nerfb200_ctx* ctx, const float* flat_params, void* stream);
+
+/* ---- a4+a5: fused encoding + 8x256 MLP forward (core/model.py:334-394) -------------------
+ * rows are generated on the fly from rays: xyz = o + t*d, dir = d. Outputs rgb[R,3] (sigmoid)
+ * and sigma[R] (relu). `flat_params` is the fp32 master block (used by NERFB200_FP32 and for
+ * the fp32 sigma/rgb heads); tensor-core precisions read the image from pack_weights.
+ * workspace: device scratch of at least nerfb200_mlp_workspace_bytes(...) bytes (may be NULL
+ * when that is 0). If `stash` is non-NULL (training), activations needed by
+ * nerfb200_mlp_backward are written there (nerfb200_mlp_stash_bytes). */
+NERFB200_API int64_t nerfb200_mlp_workspace_bytes(int64_t R, int precision, int training);
+NERFB200_API int64_t nerfb200_mlp_stash_bytes(int64_t R, int precision);
+NERFB200_API int nerfb200_mlp_forward(nerfb200_ctx* ctx, int which, int64_t B, int S, const float* rays_o,
+                         const float* rays_d, const float* t_vals, const float* flat_params,
+                         float* rgb, float* sigma, int precision, void* workspace, void* stash,
+                         void* stream);
+
+/* ---- a6: MLP backward (tf.GradientTape over core/model.py:148-170) -----------------------
+ * d_rgb[R,3], d_sigma[R] are dLoss/d(outputs). Accumulates (+=) into flat_grads (same layout as
+ * flat_params; caller zeroes it once per step). No dX for the inputs: sample positions are
+ * constants for autodiff (stop_gradient, utils/ray_utils.py:377). */
+NERFB200_API int nerfb200_mlp_backward(nerfb200_ctx* ctx, int which, int64_t B, int S, const float* rays_o,
+                          const float* rays_d, const float* t_vals, const float* flat_params,
+                          const float* d_rgb, const float* d_sigma, float* flat_grads,
+                          int precision, void* workspace, void* stash, void* stream);
+
+/* ---- a7-a9: volume-rendering integrator --------------------------------------------------
+ * sigma_to_alpha / compute_weights / post_process_model_output (utils/ray_utils.py:408-551):
+ * delta_i = t_{i+1}-t_i, delta_last = 1e10; alpha = 1-exp(-sigma*delta);
+ * w = alpha * cumprod_exclusive(1-alpha+1e-10); rgb/depth/acc = sum(w*.); white_bg: rgb += 1-acc.
+ * weights may be NULL (skips the [B,S] store). Warp-per-ray shuffle scan; 2 <= S <= 1024. */
+NERFB200_API int nerfb200_composite_fwd(int64_t B, int S, const float* sigma, const float* rgb,
+                           const float* t_vals, int white_bg, float* weights, float* pred_rgb,
+                           float* pred_depth, float* acc_map, void* stream);
+/* Backward of the above w.r.t. sigma and rgb given d_pred_rgb[B,3] (pred_depth/acc are not in
+ * the loss; acc enters through white_bg). Recomputes alpha/T from sigma,t. */
+NERFB200_API int nerfb200_composite_bwd(int64_t B, int S, const float* sigma, const float* rgb,
+                           const float* t_vals, int white_bg, const float* d_pred_rgb,
+                           float* d_sigma, float* d_rgb, void* stream);
+
+/* ---- a10: hierarchical (inverse-transform) sampler ----------------------------------------
+ * create_input_batch_fine_model (utils/ray_utils.py:276-406): pdf/cdf from (w+1e-5), upper-bound
+ * searchsorted over the Nc-1 inner CDF edges, inversion with the pdf<1e-8 mask, then
+ * sort(concat(t_coarse, t_fine)). u = u_fine[B,Nf] if non-NULL else Philox(seed, ray0+ray, j).
+ * Optional debug outputs (NULL to skip): piece_idxs[B,Nf] int32, cdf[B,Nc+1] (the fp32 CDF the
+ * indices were searched in), t_fine[B,Nf] unsorted. Nc in {32..256 step 32}, Nf multiple of 32. */
+NERFB200_API int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights,
+                         const float* bin_edges, const float* t_coarse, const float* u_fine,
+                         uint64_t seed, int64_t ray0, float* t_sorted /* [B,Nc+Nf] */,
+                         int32_t* piece_idxs, float* cdf, float* t_fine, void* stream);
+
+/* ---- a12: loss + optimiser -----------------------------------------------------------------
+ * Keras MeanSquaredError over [B,3] (core/model.py:157-168): adds mean((pred-gt)^2) to *loss and
+ * writes d_pred = 2*(pred-gt)/(B_global*3). Also accumulates the PSNRMetric state
+ * (core/ops.py:204-220): metric[0] += sum((gt-pred)^2), metric[1] += B, when metric != NULL. */
+NERFB200_API int nerfb200_mse_loss_grad(int64_t B, int64_t B_global, const float* pred_rgb, const float* rgb_gt,
+                           float* d_pred, float* loss, float* metric, void* stream);
+/* Keras Adam (OptimizerV2, beta 0.9/0.999, eps 1e-7) with ExponentialDecay(5e-4, 500000, 0.1)
+ * (core/model.py:413-418); `iterations` is the counter BEFORE the step. Fused over the flat
+ * parameter block. */
+NERFB200_API int nerfb200_adam_step(int64_t n, float* params, const float* grads, float* m, float* v,
+                       int64_t iterations, void* stream);
+
+/* ---- a15: depth map type_2 (utils/ray_utils.py:122-130) -------------------------------------
+ * z of the point o + d*depth/scale in the camera frame. */
+NERFB200_API int nerfb200_depth_type2(int H, int W, const double* K, const double* c2w, double scale_factor,
+                         const float* pred_depth, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFB200_H */

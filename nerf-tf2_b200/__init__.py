@@ -1,0 +1,17 @@
+"""
+nerf-tf2_b200: a B200-native (sm_100a) implementation of the NeRF ray-march hot path of
+thatbrguy/nerf-tf2 -- camera rays, stratified + hierarchical sampling, positional encoding,
+the coarse/fine 8x256 MLPs and the volume-rendering integrator -- behind the reference's own
+Python surface (`NeRF.fit/evaluate/predict`, the `ray_utils` functions and result dicts).
+
+Hand-written CUDA kernels in csrc/ are reached through the C ABI of include/nerfb200.h via
+ctypes. There is no CPU fallback, no Triton and no alternative backend.
+"""
+from . import _lib, data, model, ops, params, ray_utils, scene  # noqa: F401
+from ._lib import NerfB200Error  # noqa: F401
+from .data import RayDataset, create_dataset_for_render  # noqa: F401
+from .model import NeRF, PositionalEncoder, get_coarse_or_fine_model, setup_model  # noqa: F401
+from .ops import PSNRMetric, psnr_metric, psnr_metric_numpy  # noqa: F401
+from .params import load_params, make_params  # noqa: F401
+
+__version__ = "0.1.0"

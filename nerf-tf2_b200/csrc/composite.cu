@@ -1,0 +1,215 @@
+// Volume-rendering integrator: sigma_to_alpha / compute_weights / post_process_model_output
+// (utils/ray_utils.py:408-551), forward and backward.
+//
+// One warp per ray. Lane l owns the E = ceil(S/32) consecutive samples [l*E, (l+1)*E), so a warp's
+// loads cover one contiguous S*4-byte (sigma, t) or S*12-byte (rgb) span of HBM. The exclusive
+// transmittance product is a lane-local serial product followed by a 5-step shuffle scan of the
+// 32 lane totals. HBM-bound: 24*S+20 bytes per ray.
+#include "common.cuh"
+
+namespace nb {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int E>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_fwd_kernel(int64_t B, int S, const float* __restrict__ sigma, const float* __restrict__ rgb,
+                     const float* __restrict__ t_vals, int white_bg, float* __restrict__ weights,
+                     float* __restrict__ pred_rgb, float* __restrict__ pred_depth, float* __restrict__ acc_map) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (ray >= B) return;
+    const int64_t base = ray * S;
+    const int s0 = lane * E;
+
+    float t[E + 1], sg[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int s = s0 + e;
+        t[e] = s < S ? __ldg(t_vals + base + s) : 0.f;
+        sg[e] = s < S ? __ldg(sigma + base + s) : 0.f;
+    }
+    // first t of the next lane closes this lane's last interval
+    t[E] = __shfl_down_sync(0xffffffffu, t[0], 1);
+
+    float alpha[E], f[E];
+    float lane_prod = 1.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int s = s0 + e;
+        float delta = (s == S - 1) ? 1e10f : __fsub_rn(t[e + 1], t[e]);           // :462-468
+        float a = __fsub_rn(1.f, expf(-__fmul_rn(sg[e], delta)));                  // :423
+        a = s < S ? a : 0.f;
+        alpha[e] = a;
+        f[e] = s < S ? __fadd_rn(__fsub_rn(1.f, a), 1e-10f) : 1.f;                 // :480
+        lane_prod *= f[e];
+    }
+    // exclusive scan (product) of lane totals
+    float incl = lane_prod;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= v;
+    }
+    float T = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) T = 1.f;
+
+    float cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int s = s0 + e;
+        float w = alpha[e] * T;
+        T *= f[e];
+        if (s < S) {
+            if (weights) weights[base + s] = w;
+            const float* c = rgb + 3 * (base + s);
+            cr += w * __ldg(c + 0);
+            cg += w * __ldg(c + 1);
+            cb += w * __ldg(c + 2);
+            dep += w * t[e];
+            acc += w;
+        }
+    }
+    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dep = warp_sum(dep); acc = warp_sum(acc);
+    if (lane == 0) {
+        if (white_bg) {                                                            // :542-544
+            float bg = __fsub_rn(1.f, acc);
+            cr += bg; cg += bg; cb += bg;
+        }
+        pred_rgb[3 * ray + 0] = cr;
+        pred_rgb[3 * ray + 1] = cg;
+        pred_rgb[3 * ray + 2] = cb;
+        pred_depth[ray] = dep;
+        acc_map[ray] = acc;
+    }
+}
+
+// Backward w.r.t. sigma and per-sample rgb. With g_i = sum_ch dC_ch*(c_i,ch - bg):
+//   dL/dalpha_i = g_i*T_i - (sum_{k>i} g_k*w_k) / f_i      (TF's cumprod gradient: reverse cumsum / x)
+//   dL/dsigma_i = dL/dalpha_i * delta_i * exp(-sigma_i*delta_i)
+//   dL/dc_i,ch  = w_i * dC_ch
+template <int E>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_kernel(int64_t B, int S, const float* __restrict__ sigma, const float* __restrict__ rgb,
+                     const float* __restrict__ t_vals, int white_bg, const float* __restrict__ d_pred,
+                     float* __restrict__ d_sigma, float* __restrict__ d_rgb) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (ray >= B) return;
+    const int64_t base = ray * S;
+    const int s0 = lane * E;
+    const float dr = __ldg(d_pred + 3 * ray + 0), dg = __ldg(d_pred + 3 * ray + 1), db = __ldg(d_pred + 3 * ray + 2);
+    const float bg = white_bg ? 1.f : 0.f;
+
+    float t[E + 1], sg[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int s = s0 + e;
+        t[e] = s < S ? __ldg(t_vals + base + s) : 0.f;
+        sg[e] = s < S ? __ldg(sigma + base + s) : 0.f;
+    }
+    t[E] = __shfl_down_sync(0xffffffffu, t[0], 1);
+
+    float alpha[E], f[E], ex[E], delta[E];
+    float lane_prod = 1.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int s = s0 + e;
+        delta[e] = (s == S - 1) ? 1e10f : __fsub_rn(t[e + 1], t[e]);
+        ex[e] = s < S ? expf(-__fmul_rn(sg[e], delta[e])) : 1.f;
+        alpha[e] = s < S ? __fsub_rn(1.f, ex[e]) : 0.f;
+        f[e] = s < S ? __fadd_rn(__fsub_rn(1.f, alpha[e]), 1e-10f) : 1.f;
+        lane_prod *= f[e];
+    }
+    float incl = lane_prod;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= v;
+    }
+    float T = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) T = 1.f;
+
+    float Tn[E], gw[E], g[E];
+    float lane_gw = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int s = s0 + e;
+        Tn[e] = T;
+        float w = alpha[e] * T;
+        T *= f[e];
+        float gi = 0.f;
+        if (s < S) {
+            const float* c = rgb + 3 * (base + s);
+            gi = dr * (__ldg(c + 0) - bg) + dg * (__ldg(c + 1) - bg) + db * (__ldg(c + 2) - bg);
+            float* o = d_rgb + 3 * (base + s);
+            o[0] = w * dr; o[1] = w * dg; o[2] = w * db;
+        }
+        g[e] = gi;
+        gw[e] = gi * w;
+        lane_gw += gw[e];
+    }
+    // exclusive suffix sum of lane totals (reverse scan)
+    float sincl = lane_gw;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float v = __shfl_down_sync(0xffffffffu, sincl, o);
+        if (lane + o < 32) sincl += v;
+    }
+    float suffix = __shfl_down_sync(0xffffffffu, sincl, 1);
+    if (lane == 31) suffix = 0.f;
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) {
+        int s = s0 + e;
+        float dalpha = g[e] * Tn[e] - suffix / f[e];
+        suffix += gw[e];
+        if (s < S) d_sigma[base + s] = dalpha * delta[e] * ex[e];
+    }
+}
+
+static inline int pick_E(int S) { return (S + 31) / 32; }
+
+#define NB_DISPATCH_E(Eval, ...)                                   \
+    switch (Eval) {                                                \
+        case 1: { constexpr int E = 1; __VA_ARGS__; } break;       \
+        case 2: { constexpr int E = 2; __VA_ARGS__; } break;       \
+        case 3: { constexpr int E = 3; __VA_ARGS__; } break;       \
+        case 4: { constexpr int E = 4; __VA_ARGS__; } break;       \
+        case 5: case 6: { constexpr int E = 6; __VA_ARGS__; } break;   \
+        case 7: case 8: { constexpr int E = 8; __VA_ARGS__; } break;   \
+        case 9: case 10: case 11: case 12: { constexpr int E = 12; __VA_ARGS__; } break; \
+        case 13: case 14: case 15: case 16: { constexpr int E = 16; __VA_ARGS__; } break; \
+        default: { constexpr int E = 32; __VA_ARGS__; } break;     \
+    }
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+int nerfb200_composite_fwd(int64_t B, int S, const float* sigma, const float* rgb, const float* t_vals, int white_bg,
+                           float* weights, float* pred_rgb, float* pred_depth, float* acc_map, void* stream) {
+    NB_CHECK_ARG(B >= 0 && S >= 2 && S <= 1024, "composite_fwd: need 2 <= S <= 1024, got S=%d", S);
+    NB_CHECK_ARG(sigma && rgb && t_vals && pred_rgb && pred_depth && acc_map, "composite_fwd: NULL pointer");
+    if (B == 0) return 0;
+    unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    NB_DISPATCH_E(pick_E(S), (composite_fwd_kernel<E><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+                                 B, S, sigma, rgb, t_vals, white_bg, weights, pred_rgb, pred_depth, acc_map)));
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nerfb200_composite_bwd(int64_t B, int S, const float* sigma, const float* rgb, const float* t_vals, int white_bg,
+                           const float* d_pred_rgb, float* d_sigma, float* d_rgb, void* stream) {
+    NB_CHECK_ARG(B >= 0 && S >= 2 && S <= 1024, "composite_bwd: need 2 <= S <= 1024, got S=%d", S);
+    NB_CHECK_ARG(sigma && rgb && t_vals && d_pred_rgb && d_sigma && d_rgb, "composite_bwd: NULL pointer");
+    if (B == 0) return 0;
+    unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    NB_DISPATCH_E(pick_E(S), (composite_bwd_kernel<E><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+                                 B, S, sigma, rgb, t_vals, white_bg, d_pred_rgb, d_sigma, d_rgb)));
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// C-ABI entry points of the MLP: context, weight packing, forward/backward dispatch by precision.
+#include "common.cuh"
+#include "mlp.cuh"
+
+using namespace nb;
+
+extern "C" {
+
+int nerfb200_create(nerfb200_ctx** out) {
+    NB_CHECK_ARG(out != nullptr, "create: NULL output");
+    nerfb200_ctx* ctx = new nerfb200_ctx();
+    int rc = tc_create(ctx);
+    if (rc) { tc_destroy(ctx); delete ctx; return rc; }
+    *out = ctx;
+    return 0;
+}
+
+int nerfb200_destroy(nerfb200_ctx* ctx) {
+    if (!ctx) return 0;
+    tc_destroy(ctx);
+    delete ctx;
+    return 0;
+}
+
+int nerfb200_pack_weights(nerfb200_ctx* ctx, const float* flat_params, void* stream) {
+    NB_CHECK_ARG(ctx && flat_params, "pack_weights: NULL argument");
+    return tc_pack_weights(ctx, flat_params, (cudaStream_t)stream);
+}
+
+int64_t nerfb200_mlp_workspace_bytes(int64_t R, int precision, int training) {
+    if (R < 0) return -1;
+    return precision == NERFB200_FP32 ? ref_workspace_bytes(R, training) : tc_workspace_bytes(R, training);
+}
+
+int64_t nerfb200_mlp_stash_bytes(int64_t R, int precision) {
+    if (R < 0) return -1;
+    return precision == NERFB200_FP32 ? ref_stash_bytes(R) : tc_stash_bytes(R);
+}
+
+static int check_common(const char* fn, nerfb200_ctx* ctx, int which, int64_t B, int S, int precision) {
+    NB_CHECK_ARG(ctx != nullptr, "%s: NULL context", fn);
+    NB_CHECK_ARG(which == NERFB200_COARSE || which == NERFB200_FINE, "%s: which must be 0 (coarse) or 1 (fine)", fn);
+    NB_CHECK_ARG(B >= 0 && S >= 1, "%s: bad shape B=%lld S=%d", fn, (long long)B, S);
+    NB_CHECK_ARG(precision >= NERFB200_FP32 && precision <= NERFB200_FP16, "%s: unknown precision %d", fn, precision);
+    return 0;
+}
+
+int nerfb200_mlp_forward(nerfb200_ctx* ctx, int which, int64_t B, int S, const float* rays_o, const float* rays_d,
+                         const float* t_vals, const float* flat_params, float* rgb, float* sigma, int precision,
+                         void* workspace, void* stash, void* stream) {
+    int rc = check_common("mlp_forward", ctx, which, B, S, precision);
+    if (rc) return rc;
+    NB_CHECK_ARG(rays_o && rays_d && t_vals && rgb && sigma, "mlp_forward: NULL tensor");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == NERFB200_FP32) {
+        NB_CHECK_ARG(flat_params != nullptr, "mlp_forward(fp32): flat_params required");
+        return ref_forward(st, flat_params + (int64_t)which * kParamsPerModel, B, S, rays_o, rays_d, t_vals, rgb, sigma,
+                           workspace, stash);
+    }
+    return tc_forward(ctx, which, precision == NERFB200_FP16, B, S, rays_o, rays_d, t_vals, rgb, sigma, workspace, stash, st);
+}
+
+int nerfb200_mlp_backward(nerfb200_ctx* ctx, int which, int64_t B, int S, const float* rays_o, const float* rays_d,
+                          const float* t_vals, const float* flat_params, const float* d_rgb, const float* d_sigma,
+                          float* flat_grads, int precision, void* workspace, void* stash, void* stream) {
+    int rc = check_common("mlp_backward", ctx, which, B, S, precision);
+    if (rc) return rc;
+    NB_CHECK_ARG(flat_params && d_rgb && d_sigma && flat_grads, "mlp_backward: NULL tensor");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == NERFB200_FP32)
+        return ref_backward(st, flat_params + (int64_t)which * kParamsPerModel, B, S, d_rgb, d_sigma,
+                            flat_grads + (int64_t)which * kParamsPerModel, workspace, stash);
+    return tc_backward(ctx, which, precision == NERFB200_FP16, B, S, rays_o, rays_d, t_vals, flat_params, d_rgb, d_sigma,
+                       flat_grads, workspace, stash, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,609 @@
+// Fused positional-encoding + 8x256 MLP forward (core/model.py:289-394) on the 5th-generation
+// tensor cores: tcgen05.mma with fp32 accumulators in TMEM, 16-bit (bf16 or fp16) operands in
+// 128B-swizzled shared memory, weights streamed by bulk-TMA (cp.async.bulk, UBLKCP) through an
+// mbarrier ring. One persistent CTA per SM; per-sample activations never leave the SM.
+//
+// CTA layout (384 threads):
+//   warp 0      : weight producer  (one elected lane: waits ring_empty, issues cp.async.bulk)
+//   warp 1      : MMA issuer       (one elected lane: tcgen05.mma / tcgen05.commit); owns TMEM alloc
+//   warps 2-3   : idle (keep the epilogue warps aligned to TMEM lane quadrants)
+//   warps 4-7   : epilogue of row-tile slot 0 (thread = row = TMEM lane)
+//   warps 8-11  : epilogue of row-tile slot 1
+//
+// Each CTA works on TWO 128-row tiles at a time ("slots"). The MMA issuer alternates
+// (slot0, job j), (slot1, job j), (slot0, job j+1), ... so that while one slot's epilogue
+// (TMEM -> registers -> +bias, ReLU, cast -> swizzled smem = next layer's A operand) runs on the
+// CUDA cores, the other slot's layer runs on the tensor core: a layer-granular ping-pong.
+//
+// Jobs of one tile (K chunks of 64, padded columns are zero in the packed weights):
+//   J0  dense_0   A = enc_xyz(63+1)                       N=256
+//   J1-4 dense_1..4  A = act(256)                          N=256
+//   J5  dense_5   A = act(256) | enc_xyz(64)               N=256   (skip concat = one more K chunk)
+//   J6-7 dense_6,7                                          N=256   (+ sigma head in J7's epilogue, fp32)
+//   J8  dense_8   linear                                    N=256
+//   J9  dense_9   A = bott(256) | enc_dir(27+5)             N=128
+//   J10 rgb       A = act(128)                              N=16 (3 used), sigmoid in the epilogue
+//
+// Shared memory (bytes): 2 x 64 KB activations, 2 x 16 KB encodings, 4 x 16 KB weight ring, barriers.
+#include "common.cuh"
+#include "mlp.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace nb {
+
+// ---------------------------------------------------------------------------------------------
+// Packed weight image: a stream of chunks in consumption order. A chunk is [rows x 64 K] 16-bit,
+// K-major, 128 bytes per row, 16-byte units XOR-swizzled by (row & 7) (UMMA SWIZZLE_128B).
+struct Chunk {
+    uint32_t gofs;     // byte offset inside the packed image
+    uint16_t rows;     // N rows in this chunk (128 or 16)
+    uint8_t layer;     // Layer enum
+    uint8_t job;       // 0..10
+    uint8_t nh;        // which 128-wide half of N
+    uint8_t kc;        // K chunk index within the layer
+    uint8_t asrc;      // 0..3 = activation chunk, 4 = encoding buffer
+    uint8_t ksteps;    // UMMA K=16 steps in this chunk (4, or 2 for enc_dir)
+    uint8_t first;     // first K chunk of this (job, nh): accumulate = 0
+    uint8_t last;      // last chunk of the job: commit acc_full
+};
+
+constexpr int kNumJobs = 11;
+constexpr int kMaxChunks = 80;
+
+struct ChunkTable {
+    Chunk c[kMaxChunks];
+    int n;
+    int job_begin[kNumJobs + 1];
+    uint32_t bytes;
+};
+
+static ChunkTable build_chunk_table() {
+    ChunkTable t{};
+    uint32_t ofs = 0;
+    int n = 0;
+    auto add = [&](int job, int layer, int nh, int kc, int rows, int asrc, int ksteps, bool first) {
+        Chunk& c = t.c[n++];
+        c.gofs = ofs; c.rows = (uint16_t)rows; c.layer = (uint8_t)layer; c.job = (uint8_t)job; c.nh = (uint8_t)nh;
+        c.kc = (uint8_t)kc; c.asrc = (uint8_t)asrc; c.ksteps = (uint8_t)ksteps; c.first = first; c.last = 0;
+        ofs += (uint32_t)rows * 128u;
+    };
+    const int job_layer[kNumJobs] = {L0, L1, L2, L3, L4, L5, L6, L7, L8, L9, LRGB};
+    for (int j = 0; j < kNumJobs; ++j) {
+        t.job_begin[j] = n;
+        int l = job_layer[j];
+        if (j == 0) {
+            for (int nh = 0; nh < 2; ++nh) add(j, l, nh, 0, 128, 4, 4, true);
+        } else if (j == 5) {
+            for (int nh = 0; nh < 2; ++nh)
+                for (int kc = 0; kc < 5; ++kc) add(j, l, nh, kc, 128, kc < 4 ? kc : 4, 4, kc == 0);
+        } else if (j == 9) {
+            for (int kc = 0; kc < 5; ++kc) add(j, l, 0, kc, 128, kc < 4 ? kc : 4, kc < 4 ? 4 : 2, kc == 0);
+        } else if (j == 10) {
+            for (int kc = 0; kc < 2; ++kc) add(j, l, 0, kc, 16, kc, 4, kc == 0);
+        } else {
+            for (int nh = 0; nh < 2; ++nh)
+                for (int kc = 0; kc < 4; ++kc) add(j, l, nh, kc, 128, kc, 4, kc == 0);
+        }
+        t.c[n - 1].last = 1;
+    }
+    t.job_begin[kNumJobs] = n;
+    t.n = n;
+    t.bytes = ofs;
+    return t;
+}
+
+static const ChunkTable& chunk_table() {
+    static ChunkTable t = build_chunk_table();
+    return t;
+}
+
+__constant__ Chunk c_chunks[kMaxChunks];
+__constant__ int c_job_begin[kNumJobs + 1];
+
+// fp32 side parameters per model (biases of the 10 tensor-core layers + the sigma head)
+struct HeadOffsets {
+    // float offsets inside head_params
+    __host__ __device__ static constexpr int bias(int job) {   // jobs 0..8 -> 256 each, 9 -> 128, 10 -> 16 (3 used)
+        return job <= 9 ? job * 256 : 9 * 256 + 128;
+    }
+    static constexpr int wsigma = 9 * 256 + 128 + 16;   // 256 floats
+    static constexpr int bsigma = wsigma + 256;         // 1 float (+3 pad)
+    static constexpr int total = bsigma + 4;
+};
+
+template <typename T> __device__ __forceinline__ T to16(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half to16<__half>(float v) { return __float2half_rn(v); }
+
+// One thread per 16-byte unit of the packed image.
+template <typename T>
+__global__ void pack_weights_kernel(const float* __restrict__ P /* one model */, uint8_t* __restrict__ img, int nchunks) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // locate chunk by linear scan over the table (<= 80 entries)
+    int ci = -1;
+    uint32_t byte = (uint32_t)(u * 16);
+    for (int i = 0; i < nchunks; ++i) {
+        uint32_t b = c_chunks[i].gofs, e = b + c_chunks[i].rows * 128u;
+        if (byte >= b && byte < e) { ci = i; break; }
+    }
+    if (ci < 0) return;
+    const Chunk ch = c_chunks[ci];
+    uint32_t local = byte - ch.gofs;
+    int row = local >> 7;
+    int phys_unit = (local >> 4) & 7;
+    int unit = phys_unit ^ (row & 7);
+    const LayerDim dim = layer_dim(ch.layer);
+    const float* W = P + kernel_offset(ch.layer);
+    const float* bias = P + bias_offset(ch.layer);
+    (void)bias;
+    int n = ch.nh * 128 + row;
+    T vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int kl = unit * 8 + e;         // 0..63 inside the chunk
+        int k;                         // row of the Keras kernel [in,out], or -1 for zero padding
+        if (ch.layer == L0) k = kl < 63 ? kl : -1;
+        else if (ch.layer == L5) k = ch.kc < 4 ? ch.kc * 64 + kl : (kl < 63 ? 256 + kl : -1);
+        else if (ch.layer == L9) k = ch.kc < 4 ? ch.kc * 64 + kl : (kl < 27 ? 256 + kl : -1);
+        else k = ch.kc * 64 + kl;
+        float v = 0.f;
+        if (k >= 0 && k < dim.fan_in && n < dim.fan_out) v = W[(int64_t)k * dim.fan_out + n];
+        vals[e] = to16<T>(v);
+    }
+    *reinterpret_cast<uint4*>(img + byte) = *reinterpret_cast<uint4*>(vals);
+}
+
+__global__ void pack_heads_kernel(const float* __restrict__ P, float* __restrict__ hp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HeadOffsets::total) return;
+    const int job_layer[kNumJobs] = {L0, L1, L2, L3, L4, L5, L6, L7, L8, L9, LRGB};
+    float v = 0.f;
+    if (i < HeadOffsets::wsigma) {
+        int job = i < 9 * 256 ? i / 256 : (i < 9 * 256 + 128 ? 9 : 10);
+        int n = i - HeadOffsets::bias(job);
+        int l = job_layer[job];
+        if (n < layer_dim(l).fan_out) v = P[bias_offset(l) + n];
+    } else if (i < HeadOffsets::bsigma) {
+        v = P[kernel_offset(LSIGMA) + (i - HeadOffsets::wsigma)];
+    } else if (i == HeadOffsets::bsigma) {
+        v = P[bias_offset(LSIGMA)];
+    }
+    hp[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (reported as a CUDA error), never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("nerfb200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32, A/B = fmt (0 fp16, 1 bf16), both K-major, M=128.
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+template <bool kHalf> __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if constexpr (kHalf) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileRows = 128;
+constexpr int kActBytes = 4 * 16384;    // 128 rows x 256 K x 2 B, four K chunks of [128 x 64]
+constexpr int kEncBytes = 16384;        // 128 rows x 64 K x 2 B
+constexpr int kStageBytes = 16384;      // [128 N x 64 K]
+constexpr int kStages = 4;
+constexpr int kSmemAct = 0;
+constexpr int kSmemEnc = kSmemAct + 2 * kActBytes;
+constexpr int kSmemRing = kSmemEnc + 2 * kEncBytes;
+constexpr int kSmemBar = kSmemRing + kStages * kStageBytes;
+constexpr int kSmemTotal = kSmemBar + 256;
+constexpr int kThreads = 384;
+
+struct TcParams {
+    const uint8_t* wimg;     // packed weights of this model/precision
+    const float* heads;      // HeadOffsets block
+    const float* ro; const float* rd; const float* t;
+    float* rgb; float* sigma;
+    int64_t R;               // rows
+    int S;
+    int num_tiles;
+};
+
+// byte offset of (row, 16-byte unit) inside a [128 x 64] swizzled chunk
+__device__ __forceinline__ uint32_t swz(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
+
+template <bool kHalf>
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+    // barrier indices
+    auto ring_full = [&](int s) { return sbase + kSmemBar + 8 * s; };
+    auto ring_empty = [&](int s) { return sbase + kSmemBar + 8 * (kStages + s); };
+    auto act_ready = [&](int t) { return sbase + kSmemBar + 8 * (2 * kStages + t); };
+    auto acc_full = [&](int t) { return sbase + kSmemBar + 8 * (2 * kStages + 2 + t); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(act_ready(t), kTileRows); mbar_init(acc_full(t), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int pairs = (p.num_tiles + 1) >> 1;
+    constexpr int fmt = kHalf ? 0 : 1;
+
+    if (warp == 0) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+                for (int j = 0; j < kNumJobs; ++j) {
+                    for (int t = 0; t < 2; ++t) {
+                        if (pr * 2 + t >= p.num_tiles) continue;
+                        for (int ci = c_job_begin[j]; ci < c_job_begin[j + 1]; ++ci) {
+                            const Chunk ch = c_chunks[ci];
+                            mbar_wait(ring_empty(stage), phase ^ 1);
+                            uint32_t bytes = (uint32_t)ch.rows * 128u;
+                            mbar_expect_tx(ring_full(stage), bytes);
+                            bulk_g2s(sbase + kSmemRing + stage * kStageBytes, p.wimg + ch.gofs, bytes, ring_full(stage));
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            uint32_t act_phase[2] = {0, 0};
+            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+                for (int j = 0; j < kNumJobs; ++j) {
+                    for (int t = 0; t < 2; ++t) {
+                        if (pr * 2 + t >= p.num_tiles) continue;
+                        mbar_wait(act_ready(t), act_phase[t]);
+                        act_phase[t] ^= 1;
+                        tc_fence_after();
+                        const uint32_t a_act = sbase + kSmemAct + t * kActBytes;
+                        const uint32_t a_enc = sbase + kSmemEnc + t * kEncBytes;
+                        for (int ci = c_job_begin[j]; ci < c_job_begin[j + 1]; ++ci) {
+                            const Chunk ch = c_chunks[ci];
+                            mbar_wait(ring_full(stage), phase);
+                            tc_fence_after();
+                            const uint32_t a_addr = ch.asrc < 4 ? a_act + ch.asrc * 16384u : a_enc;
+                            const uint32_t b_addr = sbase + kSmemRing + stage * kStageBytes;
+                            const uint32_t d_addr = tmem_base + (uint32_t)(t * 256 + ch.nh * 128);
+                            const uint32_t idesc = umma_idesc(fmt, ch.rows);
+                            const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+                            for (int k = 0; k < ch.ksteps; ++k) {
+                                // advance 16 K elements = 32 bytes inside the 128-byte swizzle row (>>4 => +2)
+                                umma_f16(d_addr, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                                         (ch.first && k == 0) ? 0u : 1u);
+                            }
+                            umma_commit(ring_empty(stage));
+                            if (ch.last) umma_commit(acc_full(t));
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warps =====================
+        const int t = (warp - 4) >> 2;                 // slot
+        const int q = warp & 3;                        // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;                 // row inside the tile == TMEM lane
+        uint8_t* act = smem + kSmemAct + t * kActBytes;
+        uint8_t* enc = smem + kSmemEnc + t * kEncBytes;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+        uint32_t acc_phase = 0;
+        const float4* heads4 = reinterpret_cast<const float4*>(p.heads);
+
+        for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+            const int tile = pr * 2 + t;
+            if (tile >= p.num_tiles) continue;
+            const int64_t grow = (int64_t)tile * kTileRows + row;
+            const bool valid = grow < p.R;
+            const int64_t lrow = valid ? grow : p.R - 1;
+            const int64_t ray = lrow / p.S;
+            const float tv = __ldg(p.t + lrow);
+            float dir[3], xyz[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                dir[d] = __ldg(p.rd + 3 * ray + d);
+                xyz[d] = __fadd_rn(__ldg(p.ro + 3 * ray + d), __fmul_rn(tv, dir[d]));   // utils/ray_utils.py:251
+            }
+            // ---- positional encoding of xyz (L=10) -> enc buffer, 64 columns (col 63 = 0)
+            {
+                float e[64];
+                e[0] = xyz[0]; e[1] = xyz[1]; e[2] = xyz[2];
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int l = 0; l < 10; ++l) {
+                        float arg = __fmul_rn(xyz[d], __fmul_rn((float)(1 << l), 3.14159274101257324f));
+                        float sn, cs;
+                        sincosf(arg, &sn, &cs);
+                        e[3 + d * 20 + 2 * l] = sn;
+                        e[3 + d * 20 + 2 * l + 1] = cs;
+                    }
+                e[63] = 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint4 v;
+                    v.x = pack2<kHalf>(e[8 * u + 0], e[8 * u + 1]);
+                    v.y = pack2<kHalf>(e[8 * u + 2], e[8 * u + 3]);
+                    v.z = pack2<kHalf>(e[8 * u + 4], e[8 * u + 5]);
+                    v.w = pack2<kHalf>(e[8 * u + 6], e[8 * u + 7]);
+                    *reinterpret_cast<uint4*>(enc + swz(row, u)) = v;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(act_ready(t));
+
+            float sig_acc = 0.f;
+            for (int j = 0; j < kNumJobs; ++j) {
+                mbar_wait(acc_full(t), acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                if (j < 10) {
+                    const int N = j == 9 ? 128 : 256;
+                    const bool relu = j != 8;
+                    const float4* b4 = heads4 + HeadOffsets::bias(j) / 4;
+                    const float4* ws4 = heads4 + HeadOffsets::wsigma / 4;
+                    for (int c0 = 0; c0 < N; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_row + (uint32_t)c0, r);
+                        float4 bb[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) bb[i] = __ldg(b4 + (c0 >> 2) + i);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb[i].x;
+                            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb[i].y;
+                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb[i].z;
+                            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb[i].w;
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (j == 7) {   // sigma head on the fp32 activations (core/model.py:375)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float4 w = __ldg(ws4 + (c0 >> 2) + i);
+                                sig_acc = fmaf(v[4 * i + 0], w.x, sig_acc);
+                                sig_acc = fmaf(v[4 * i + 1], w.y, sig_acc);
+                                sig_acc = fmaf(v[4 * i + 2], w.z, sig_acc);
+                                sig_acc = fmaf(v[4 * i + 3], w.w, sig_acc);
+                            }
+                        }
+                        uint8_t* chunk = act + (c0 >> 6) * 16384;
+                        const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint4 o;
+                            o.x = pack2<kHalf>(v[8 * u + 0], v[8 * u + 1]);
+                            o.y = pack2<kHalf>(v[8 * u + 2], v[8 * u + 3]);
+                            o.z = pack2<kHalf>(v[8 * u + 4], v[8 * u + 5]);
+                            o.w = pack2<kHalf>(v[8 * u + 6], v[8 * u + 7]);
+                            *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = o;
+                        }
+                    }
+                    if (j == 5) {
+                        // dense_5 has consumed enc_xyz: reuse the encoding buffer for enc_dir (L=4), cols 27..63 = 0
+                        float e[32];
+                        e[0] = dir[0]; e[1] = dir[1]; e[2] = dir[2];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+#pragma unroll
+                            for (int l = 0; l < 4; ++l) {
+                                float arg = __fmul_rn(dir[d], __fmul_rn((float)(1 << l), 3.14159274101257324f));
+                                float sn, cs;
+                                sincosf(arg, &sn, &cs);
+                                e[3 + d * 8 + 2 * l] = sn;
+                                e[3 + d * 8 + 2 * l + 1] = cs;
+                            }
+#pragma unroll
+                        for (int i = 27; i < 32; ++i) e[i] = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+                            if (u < 4) {
+                                v4.x = pack2<kHalf>(e[8 * u + 0], e[8 * u + 1]);
+                                v4.y = pack2<kHalf>(e[8 * u + 2], e[8 * u + 3]);
+                                v4.z = pack2<kHalf>(e[8 * u + 4], e[8 * u + 5]);
+                                v4.w = pack2<kHalf>(e[8 * u + 6], e[8 * u + 7]);
+                            }
+                            *reinterpret_cast<uint4*>(enc + swz(row, u)) = v4;
+                        }
+                    }
+                    if (j == 7 && valid) {
+                        float s = sig_acc + __ldg(p.heads + HeadOffsets::bsigma);
+                        p.sigma[grow] = fmaxf(s, 0.f);
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(act_ready(t));
+                } else {
+                    // rgb head: 16 accumulator columns, 3 used (core/model.py:387)
+                    uint32_t r[32];
+                    tmem_ld32(tmem_row, r);   // columns 16..31 hold stale data from dense_9; ignored
+                    tmem_ld_wait();
+                    if (valid) {
+                        const float* b = p.heads + HeadOffsets::bias(10);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float x = __uint_as_float(r[c]) + __ldg(b + c);
+                            p.rgb[3 * grow + c] = 1.f / (1.f + expf(-x));
+                        }
+                    }
+                    tc_fence_before();
+                }
+            }
+        }
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+static bool g_table_uploaded = false;
+static int upload_table() {
+    if (g_table_uploaded) return 0;
+    const ChunkTable& t = chunk_table();
+    NB_CUDA(cudaMemcpyToSymbol(c_chunks, t.c, sizeof(Chunk) * kMaxChunks));
+    NB_CUDA(cudaMemcpyToSymbol(c_job_begin, t.job_begin, sizeof(int) * (kNumJobs + 1)));
+    g_table_uploaded = true;
+    return 0;
+}
+
+int tc_create(nerfb200_ctx* ctx) {
+    NB_CUDA(cudaGetDevice(&ctx->device));
+    NB_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const ChunkTable& t = chunk_table();
+    for (int pz = 0; pz < 2; ++pz)
+        for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc(&ctx->packed[pz][m], t.bytes));
+    for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc((void**)&ctx->head_params[m], HeadOffsets::total * sizeof(float)));
+    int rc = upload_table();
+    if (rc) return rc;
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    return 0;
+}
+
+void tc_destroy(nerfb200_ctx* ctx) {
+    for (int pz = 0; pz < 2; ++pz)
+        for (int m = 0; m < 2; ++m) if (ctx->packed[pz][m]) cudaFree(ctx->packed[pz][m]);
+    for (int m = 0; m < 2; ++m) if (ctx->head_params[m]) cudaFree(ctx->head_params[m]);
+}
+
+int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st) {
+    const ChunkTable& t = chunk_table();
+    int64_t units = t.bytes / 16;
+    for (int m = 0; m < 2; ++m) {
+        const float* P = flat_params + (int64_t)m * kParamsPerModel;
+        pack_weights_kernel<__nv_bfloat16><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m], t.n);
+        pack_weights_kernel<__half><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m], t.n);
+        pack_heads_kernel<<<(HeadOffsets::total + 255) / 256, 256, 0, st>>>(P, ctx->head_params[m]);
+    }
+    NB_LAUNCH_CHECK();
+    ctx->packed_valid = true;
+    return 0;
+}
+
+int64_t tc_workspace_bytes(int64_t, int) { return 0; }
+int64_t tc_stash_bytes(int64_t) { return 0; }
+
+int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
+               float* rgb, float* sigma, void* workspace, void* stash, cudaStream_t st) {
+    (void)workspace;
+    if (!ctx->packed_valid) { set_error("mlp_forward: pack_weights has not been called"); return NERFB200_ESTATE; }
+    if (stash) { set_error("mlp_forward: training stash is not supported by the tensor-core path yet"); return NERFB200_ENOTSUP; }
+    const int64_t R = B * S;
+    if (R == 0) return 0;
+    NB_CHECK_ARG((R + kTileRows - 1) / kTileRows < (int64_t)1 << 30, "mlp_forward: too many rows");
+    TcParams p;
+    p.wimg = (const uint8_t*)ctx->packed[half ? 1 : 0][which];
+    p.heads = ctx->head_params[which];
+    p.ro = ro; p.rd = rd; p.t = t; p.rgb = rgb; p.sigma = sigma; p.R = R; p.S = S;
+    p.num_tiles = (int)((R + kTileRows - 1) / kTileRows);
+    int pairs = (p.num_tiles + 1) / 2;
+    int grid = pairs < ctx->num_sms ? pairs : ctx->num_sms;
+    if (half) mlp_tc_forward_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(p);
+    else mlp_tc_forward_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(p);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int tc_backward(nerfb200_ctx*, int, int, int64_t, int, const float*, const float*, const float*, const float*,
+                const float*, const float*, float*, void*, void*, cudaStream_t) {
+    set_error("mlp_backward: tensor-core backward not implemented yet; use NERFB200_FP32");
+    return NERFB200_ENOTSUP;
+}
+
+}  // namespace nb

@@ -1,0 +1,79 @@
+// Loss, metric state and the fused Adam step of NeRF.train_step (core/model.py:127-180, :413-418).
+#include "common.cuh"
+
+#include <math.h>
+
+namespace nb {
+
+// Keras MeanSquaredError over [B,3]: loss += sum((pred-gt)^2)/(B_global*3); d_pred = 2*(pred-gt)/(B_global*3).
+// PSNRMetric.update_state (core/ops.py:204-220): metric[0] += sum((gt-pred)^2), metric[1] += B.
+__global__ void mse_loss_grad_kernel(int64_t B, float inv_n, const float* __restrict__ pred, const float* __restrict__ gt,
+                                     float* __restrict__ d_pred, float* __restrict__ loss, float* __restrict__ metric) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float sq = 0.f;
+    if (i < B * 3) {
+        float d = pred[i] - gt[i];
+        if (d_pred) d_pred[i] = 2.f * d * inv_n;
+        sq = d * d;
+    }
+    sq = warp_sum(sq);
+    __shared__ float part[8];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) part[w] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += part[k];
+        if (loss) atomicAdd(loss, s * inv_n);
+        if (metric) {
+            atomicAdd(metric, s);
+            if (blockIdx.x == 0) atomicAdd(metric + 1, (float)B);
+        }
+    }
+}
+
+// Keras OptimizerV2 Adam._resource_apply_dense (non-amsgrad): SURVEY.md Appendix A.
+__global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, float lr_t, float b1, float b2, float eps) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    float mi = __fadd_rn(__fmul_rn(m[i], b1), __fmul_rn(gi, 1.f - b1));
+    float vi = __fadd_rn(__fmul_rn(v[i], b2), __fmul_rn(__fmul_rn(gi, gi), 1.f - b2));
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = __fsub_rn(p[i], __fdiv_rn(__fmul_rn(lr_t, mi), __fadd_rn(__fsqrt_rn(vi), eps)));
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+int nerfb200_mse_loss_grad(int64_t B, int64_t B_global, const float* pred_rgb, const float* rgb_gt, float* d_pred,
+                           float* loss, float* metric, void* stream) {
+    NB_CHECK_ARG(B >= 0 && B_global >= B && pred_rgb && rgb_gt, "mse_loss_grad: bad arguments");
+    if (B == 0) return 0;
+    float inv_n = 1.0f / (float)(B_global * 3);
+    mse_loss_grad_kernel<<<(unsigned)((B * 3 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, inv_n, pred_rgb, rgb_gt,
+                                                                                          d_pred, loss, metric);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nerfb200_adam_step(int64_t n, float* params, const float* grads, float* m, float* v, int64_t iterations,
+                       void* stream) {
+    NB_CHECK_ARG(n >= 0 && params && grads && m && v && iterations >= 0, "adam_step: bad arguments");
+    if (n == 0) return 0;
+    const double beta1 = 0.9, beta2 = 0.999;
+    double t = (double)(iterations + 1);
+    float lr = (float)(5e-4 * pow(0.1, (double)iterations / 500000.0));       // ExponentialDecay, staircase=False
+    float lr_t = lr * (float)sqrt(1.0 - pow(beta2, t)) / (float)(1.0 - pow(beta1, t));
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, params, grads, m, v, lr_t, 0.9f, 0.999f,
+                                                                             1e-7f);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,530 @@
+"""
+Host-side mirror of the reference's `nerf/core/model.py`: the `NeRF` model with its Keras-shaped
+surface (`fit` / `evaluate` / `predict`, `train_step` / `test_step` / `predict_step`, `call`,
+`forward`, `compile`, `trainable_variables`, `optimizer.variables()`), `setup_model`,
+`get_coarse_or_fine_model` and `PositionalEncoder`. Everything numeric runs in the sm_100a
+kernels behind the C ABI; torch only owns device memory, streams and the process group.
+
+Parameters are ONE flat fp32 device buffer (coarse model then fine model, variables in Keras
+creation order, kernels [in,out] row-major): the 48 `trainable_variables` are views into it, the
+gradient is one flat buffer (a single NCCL all-reduce in data-parallel training)
+and Adam is one fused launch.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, ops, ray_utils
+from ._lib import BF16, COARSE, FINE, FP16, FP32, PARAMS_PER_MODEL, PARAMS_TOTAL, check, load, ptr, stream_ptr
+from .data import RayDataset
+
+LAYER_NAMES = [f"dense_{i}" for i in range(8)] + ["sigma", "dense_8", "dense_9", "rgb"]
+LAYER_SHAPES = {
+    "dense_0": (63, 256), "dense_1": (256, 256), "dense_2": (256, 256), "dense_3": (256, 256),
+    "dense_4": (256, 256), "dense_5": (319, 256), "dense_6": (256, 256), "dense_7": (256, 256),
+    "sigma": (256, 1), "dense_8": (256, 256), "dense_9": (283, 128), "rgb": (128, 3),
+}
+
+
+def variable_names(model_name):
+    """`{model}/dense_i/kernel:0`-style names without the `:0` (core/model.py:367-386)."""
+    out = []
+    for ln in LAYER_NAMES:
+        out += [f"{model_name}/{ln}/kernel", f"{model_name}/{ln}/bias"]
+    return out
+
+
+def glorot_uniform_params(seed):
+    """Keras defaults for Dense: glorot_uniform kernels, zero biases; flat [PARAMS_TOTAL] fp32."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for _ in ("coarse", "fine"):
+        for ln in LAYER_NAMES:
+            fi, fo = LAYER_SHAPES[ln]
+            lim = math.sqrt(6.0 / (fi + fo))
+            parts.append(rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32).reshape(-1))
+            parts.append(np.zeros((fo,), dtype=np.float32))
+    flat = np.concatenate(parts)
+    assert flat.shape[0] == PARAMS_TOTAL
+    return flat
+
+
+class PositionalEncoder:
+    """PositionalEncoder (core/model.py:289-332). Standalone layer object for API parity; inside
+    the fused MLP kernel the encoding is computed on chip and never written to HBM."""
+
+    def __init__(self, L, name=None):
+        self.L = L
+        self.name = name
+
+    def __call__(self, x):
+        return ray_utils.positional_encode(x.contiguous(), self.L)
+
+    call = __call__
+
+
+class Variable:
+    """A named view into the flat parameter buffer (stands in for tf.Variable)."""
+
+    def __init__(self, name, view):
+        self.name = name
+        self._view = view
+        self.shape = tuple(view.shape)
+
+    def numpy(self):
+        return self._view.detach().cpu().numpy().copy()
+
+    def value(self):
+        return self._view
+
+    def assign(self, arr):
+        self._view.copy_(torch.as_tensor(np.asarray(arr), dtype=torch.float32).reshape(self.shape))
+
+
+class SubModel:
+    """The coarse or the fine 8x256 MLP (get_coarse_or_fine_model, core/model.py:334-394):
+    callable on (xyz[R,3], dirs[R,3]) -> (rgb[R,3], sigma[R,1])."""
+
+    def __init__(self, nerf, which, name):
+        self._nerf, self.which, self.name = nerf, which, name
+
+    @property
+    def trainable_variables(self):
+        return self._nerf._variables[self.which * 24:(self.which + 1) * 24]
+
+    variables = weights = trainable_variables
+
+    def get_weights(self):
+        return [v.numpy() for v in self.trainable_variables]
+
+    def set_weights(self, arrays):
+        assert len(arrays) == 24
+        for v, a in zip(self.trainable_variables, arrays):
+            v.assign(a)
+        self._nerf._dirty = True
+
+    def __call__(self, inputs, precision=None):
+        xyz, dirs = inputs
+        R = xyz.shape[0]
+        t0 = torch.zeros((R, 1), device=xyz.device, dtype=torch.float32)
+        # a row is a 1-sample ray with o = xyz, t = 0: o + 0*d == o exactly
+        rgb, sigma = self._nerf._mlp(self.which, xyz.contiguous(), dirs.contiguous(), t0, precision=precision)
+        return rgb, sigma.reshape(R, 1)
+
+
+class _Adam:
+    """Keras Adam + ExponentialDecay(5e-4, 500000, 0.1) state (core/model.py:413-418)."""
+
+    def __init__(self, nerf):
+        self._nerf = nerf
+        self.iterations = 0
+        self.m = torch.zeros_like(nerf.flat_params)
+        self.v = torch.zeros_like(nerf.flat_params)
+
+    def learning_rate(self, step=None):
+        step = self.iterations if step is None else step
+        return 5e-4 * (0.1 ** (step / 500000.0))
+
+    def variables(self):
+        """[iter, m x48, v x48] -- the order CustomSaver/set_everything rely on (core/ops.py:146-149)."""
+        out = [np.int64(self.iterations)]
+        for buf in (self.m, self.v):
+            for var in self._nerf._variables:
+                out.append(buf[var._ofs:var._ofs + var._n].reshape(var.shape).cpu().numpy().copy())
+        return out
+
+    def set_weights(self, weights):
+        self.iterations = int(weights[0])
+        vs = self._nerf._variables
+        for k, buf in enumerate((self.m, self.v)):
+            for i, var in enumerate(vs):
+                arr = torch.as_tensor(np.asarray(weights[1 + k * len(vs) + i]), dtype=torch.float32)
+                buf[var._ofs:var._ofs + var._n].copy_(arr.reshape(-1))
+
+    def apply_gradients(self, flat_grads):
+        n = self._nerf.flat_params.numel()
+        check(load().nerfb200_adam_step(n, ptr(self._nerf.flat_params), ptr(flat_grads), ptr(self.m), ptr(self.v),
+                                        self.iterations, stream_ptr()), "adam_step")
+        self.iterations += 1
+        self._nerf._dirty = True
+
+
+class History:
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+
+class NeRF:
+    """NeRF(Model) (core/model.py:18-287)."""
+
+    def __init__(self, params, precision="bf16", train_precision=None, seed=0, device=None,
+                 rng_seed=0, render_chunk=32768):
+        _lib.require_cuda()
+        load()
+        self.params = params
+        self.white_bg = params.system.white_bg
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else precision
+        tp = precision if train_precision is None else train_precision
+        self.train_precision = _lib.PRECISIONS[tp] if isinstance(tp, str) else tp
+        self.rng_seed = rng_seed
+        self.render_chunk = render_chunk
+        self.val_cache = []
+        with torch.cuda.device(self.device):
+            self.flat_params = torch.from_numpy(glorot_uniform_params(seed)).to(self.device)
+            self.flat_grads = torch.zeros_like(self.flat_params)
+            h = C.c_void_p()
+            check(load().nerfb200_create(C.byref(h)), "create")
+            self._ctx = h
+        offs = _lib.param_offsets()
+        self._variables = []
+        for mi, mname in enumerate(("coarse", "fine")):
+            names = variable_names(mname)
+            for vi, nm in enumerate(names):
+                ln = LAYER_NAMES[vi // 2]
+                fi, fo = LAYER_SHAPES[ln]
+                shape = (fi, fo) if vi % 2 == 0 else (fo,)
+                o = mi * PARAMS_PER_MODEL + offs[vi]
+                n = int(np.prod(shape))
+                var = Variable(nm, self.flat_params[o:o + n].view(shape))
+                var._ofs, var._n = o, n
+                self._variables.append(var)
+        self.coarse_model = SubModel(self, COARSE, "coarse")
+        self.fine_model = SubModel(self, FINE, "fine")
+        self._dirty = True
+        self._ws = {}
+        self.optimizer = None
+        self.metrics = []
+        self.process_group = None
+        self.world_size, self.rank = 1, 0
+        self._step_counter = 0
+        self.last_loss = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                load().nerfb200_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ Keras-shaped plumbing
+    @property
+    def trainable_variables(self):
+        return self._variables
+
+    def compile(self, optimizer=None, metrics=None, run_eagerly=False):
+        """Model.compile as used by setup_model (core/model.py:422-427). The optimiser is always the
+        reference's Adam + ExponentialDecay; `optimizer` is accepted for signature parity."""
+        self.optimizer = _Adam(self)
+        self.metrics = list(metrics) if metrics is not None else [ops.PSNRMetric()]
+
+    def set_distributed(self, process_group=None):
+        """Data-parallel training over torch.distributed (NCCL on GPUs): the 4096-ray batch is split
+        across ranks and the flat gradient is all-reduced once per step."""
+        import torch.distributed as dist
+        self.process_group = process_group if process_group is not None else dist.group.WORLD
+        self.world_size = dist.get_world_size(self.process_group)
+        self.rank = dist.get_rank(self.process_group)
+
+    def set_flat_params(self, flat):
+        self.flat_params.copy_(torch.as_tensor(flat, dtype=torch.float32).to(self.device))
+        self._dirty = True
+
+    def set_weights_from_dict(self, w):
+        """Load a {name: array} dict keyed like variable_names()."""
+        for var in self._variables:
+            var.assign(w[var.name])
+        self._dirty = True
+
+    def _sync_packed(self):
+        if self._dirty:
+            check(load().nerfb200_pack_weights(self._ctx, ptr(self.flat_params), stream_ptr()), "pack_weights")
+            self._dirty = False
+
+    def _scratch(self, key, nbytes):
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 16), device=self.device, dtype=torch.uint8)
+            self._ws[key] = buf
+        return buf
+
+    # ------------------------------------------------------------------------------ MLP calls
+    def _mlp(self, which, rays_o, rays_d, t_vals, precision=None, stash=None):
+        precision = self.precision if precision is None else precision
+        B, S = t_vals.shape
+        R = B * S
+        rgb = torch.empty((R, 3), device=self.device, dtype=torch.float32)
+        sigma = torch.empty((R,), device=self.device, dtype=torch.float32)
+        self._sync_packed()
+        training = stash is not None
+        wsb = load().nerfb200_mlp_workspace_bytes(R, precision, 0)
+        ws = self._scratch("mlp_ws", wsb) if (wsb > 0 and not training) else None
+        check(load().nerfb200_mlp_forward(self._ctx, which, B, S, ptr(rays_o), ptr(rays_d), ptr(t_vals.contiguous()),
+                                          ptr(self.flat_params), ptr(rgb), ptr(sigma), precision,
+                                          ptr(ws, torch.uint8, allow_none=True),
+                                          ptr(stash, torch.uint8, allow_none=True), stream_ptr()), "mlp_forward")
+        return rgb, sigma
+
+    def _mlp_backward(self, which, rays_o, rays_d, t_vals, d_rgb, d_sigma, precision, stash):
+        B, S = t_vals.shape
+        wsb = load().nerfb200_mlp_workspace_bytes(B * S, precision, 1)
+        ws = self._scratch("mlp_bwd_ws", wsb) if wsb > 0 else None
+        check(load().nerfb200_mlp_backward(self._ctx, which, B, S, ptr(rays_o), ptr(rays_d), ptr(t_vals.contiguous()),
+                                           ptr(self.flat_params), ptr(d_rgb), ptr(d_sigma), ptr(self.flat_grads),
+                                           precision, ptr(ws, torch.uint8, allow_none=True),
+                                           ptr(stash, torch.uint8, allow_none=True), stream_ptr()), "mlp_backward")
+
+    # ---------------------------------------------------------------------------- the ray march
+    def forward(self, rays_o, rays_d, near, far, u_coarse=None, u_fine=None, ray0=0, precision=None,
+                need_weights=True, _train=None):
+        """NeRF.forward (core/model.py:57-125): stratified sampling -> coarse MLP -> compositing ->
+        hierarchical sampling -> fine MLP -> compositing. Returns (post_proc_CM, post_proc_FM).
+        `u_coarse`/`u_fine` are the fixed uniforms of the parity contract; when None the kernels
+        draw Philox uniforms keyed by (rng_seed, step, ray0 + ray)."""
+        s = self.params.sampling
+        precision = self.precision if precision is None else precision
+        rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
+        seed = (self.rng_seed << 20) ^ self._step_counter
+        t_c, edges = ray_utils.sample_coarse(s.N_coarse, s.lin_inv_depth, s.perturb, near, far, u_coarse, seed, ray0)
+        st_c = st_f = None
+        if _train is not None:
+            R_c, R_f = t_c.shape[0] * s.N_coarse, t_c.shape[0] * (s.N_coarse + s.N_fine)
+            st_c = self._scratch("stash_c", load().nerfb200_mlp_stash_bytes(R_c, precision))
+            st_f = self._scratch("stash_f", load().nerfb200_mlp_stash_bytes(R_f, precision))
+        rgb_c, sig_c = self._mlp(COARSE, rays_o, rays_d, t_c, precision, st_c)
+        pp_c = ray_utils.post_process_model_output(rgb_c, sig_c, t_c, self.white_bg)
+        t_f = ray_utils.sample_fine(s.N_fine, pp_c["weights"], edges, t_c, u_fine, seed, ray0)
+        rgb_f, sig_f = self._mlp(FINE, rays_o, rays_d, t_f, precision, st_f)
+        pp_f = ray_utils.post_process_model_output(rgb_f, sig_f, t_f, self.white_bg, need_weights=need_weights)
+        if _train is not None:
+            _train.update(dict(t_c=t_c, t_f=t_f, rgb_c=rgb_c, sig_c=sig_c, rgb_f=rgb_f, sig_f=sig_f,
+                               st_c=st_c, st_f=st_f))
+        return pp_c, pp_f
+
+    def call(self, inputs):
+        """NeRF.call (core/model.py:36-55): inputs[0] = (rays_o, rays_d, near, far)."""
+        ro, rd, near, far = (self._to_device(a) for a in inputs[0])
+        return self.forward(ro, rd, near, far)
+
+    __call__ = call
+
+    def _to_device(self, a):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a.to(dtype=torch.float32).contiguous()
+            return a.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+
+    # -------------------------------------------------------------------------------- training
+    def _loss_and_grads(self, rays_o, rays_d, near, far, rgb, u_coarse=None, u_fine=None, ray0=0,
+                        global_batch=None):
+        """Forward + backward of train_step (core/model.py:148-170) into self.flat_grads (local sum).
+        Returns the device tensor [loss] (this rank's share of the global mean losses)."""
+        prec = self.train_precision
+        B = rays_o.shape[0]
+        Bg = B * self.world_size if global_batch is None else global_batch
+        tr = {}
+        pp_c, pp_f = self.forward(rays_o, rays_d, near, far, u_coarse, u_fine, ray0, precision=prec, _train=tr)
+        loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        d_c = torch.empty((B, 3), device=self.device, dtype=torch.float32)
+        d_f = torch.empty((B, 3), device=self.device, dtype=torch.float32)
+        metric = self.metrics[0] if self.metrics else None
+        if metric is not None:
+            metric._ensure(self.device)
+        lib = load()
+        check(lib.nerfb200_mse_loss_grad(B, Bg, ptr(pp_c["pred_rgb"]), ptr(rgb), ptr(d_c), ptr(loss),
+                                         C.c_void_p(0), stream_ptr()), "mse_loss_grad")
+        check(lib.nerfb200_mse_loss_grad(B, Bg, ptr(pp_f["pred_rgb"]), ptr(rgb), ptr(d_f), ptr(loss),
+                                         ptr(metric.state) if metric is not None else C.c_void_p(0),
+                                         stream_ptr()), "mse_loss_grad")
+        self.flat_grads.zero_()
+        ds, dr = ray_utils.composite_backward(tr["rgb_c"], tr["sig_c"], tr["t_c"], self.white_bg, d_c)
+        self._mlp_backward(COARSE, rays_o, rays_d, tr["t_c"], dr, ds, prec, tr["st_c"])
+        ds, dr = ray_utils.composite_backward(tr["rgb_f"], tr["sig_f"], tr["t_f"], self.white_bg, d_f)
+        self._mlp_backward(FINE, rays_o, rays_d, tr["t_f"], dr, ds, prec, tr["st_f"])
+        return loss, pp_c, pp_f
+
+    def train_step(self, data, u_coarse=None, u_fine=None, ray0=0):
+        """NeRF.train_step (core/model.py:127-180). `data` = ((rays_o, rays_d, near, far), (rgb,)) --
+        this rank's shard of the batch when data-parallel."""
+        if self.optimizer is None:
+            self.compile()
+        (ro, rd, near, far), (rgb,) = data
+        ro, rd, near, far, rgb = (self._to_device(a) for a in (ro, rd, near, far, rgb))
+        loss, _, _ = self._loss_and_grads(ro, rd, near, far, rgb, u_coarse, u_fine, ray0)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grads, group=self.process_group)     # one flat 4.77 MB buffer
+            dist.all_reduce(loss, group=self.process_group)
+        self.optimizer.apply_gradients(self.flat_grads)
+        self._step_counter += 1
+        self.last_loss = loss
+        return {m.name: m.result() for m in self.metrics}
+
+    def test_step(self, data, u_coarse=None, u_fine=None):
+        """NeRF.test_step (core/model.py:182-223): forward + metric update on the fine output."""
+        (ro, rd, near, far), (rgb,) = data
+        ro, rd, near, far, rgb = (self._to_device(a) for a in (ro, rd, near, far, rgb))
+        _, pp_f = self.forward(ro, rd, near, far, u_coarse, u_fine, need_weights=False)
+        for m in self.metrics:
+            m.update_state(rgb, pp_f["pred_rgb"])
+        return {m.name: m.result() for m in self.metrics}
+
+    def predict_step(self, data):
+        """NeRF.predict_step (core/model.py:225-237)."""
+        return self(data)
+
+    def _metric_allreduce(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            for m in self.metrics:
+                if m.state is not None:
+                    dist.all_reduce(m.state, group=self.process_group)
+
+    def fit(self, x=None, epochs=1, steps_per_epoch=None, validation_data=None, validation_freq=1,
+            callbacks=None, initial_epoch=0, verbose=0, **_):
+        """Model.fit as driven by main/train.py:57-64: `steps_per_epoch` train_steps per epoch over
+        the (repeating) dataset, metrics reset per epoch, validation every `validation_freq` epochs."""
+        if self.optimizer is None:
+            self.compile()
+        hist = History()
+        it = iter(x)
+        for cb in callbacks or []:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+        for epoch in range(initial_epoch, epochs):
+            for m in self.metrics:
+                m.reset_states()
+            steps, logs = 0, {}
+            while steps_per_epoch is None or steps < steps_per_epoch:
+                try:
+                    batch = next(it)
+                except StopIteration:
+                    if steps_per_epoch is None:
+                        break
+                    it = iter(x)
+                    batch = next(it)
+                self.train_step(batch)
+                steps += 1
+            self._metric_allreduce()
+            logs = {m.name: m.result() for m in self.metrics}
+            if self.last_loss is not None:
+                logs["loss"] = float(self.last_loss.item())
+            if validation_data is not None and (epoch + 1) % validation_freq == 0:
+                val = self.evaluate(validation_data, return_dict=True)
+                logs.update({f"val_{k}": v for k, v in val.items()})
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            for cb in callbacks or []:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+            if verbose:
+                print(f"epoch {epoch + 1}/{epochs} " + " ".join(f"{k}={v:.4f}" for k, v in logs.items()))
+            if steps_per_epoch is None:
+                it = iter(x)
+        return hist
+
+    def evaluate(self, x=None, return_dict=False, **_):
+        """Model.evaluate: test_step over the dataset; returns the PSNRMetric value."""
+        if not self.metrics:
+            self.compile()
+        for m in self.metrics:
+            m.reset_states()
+        for batch in x:
+            self.test_step(batch)
+        self._metric_allreduce()
+        res = {m.name: m.result() for m in self.metrics}
+        return res if return_dict else (list(res.values())[0] if len(res) == 1 else list(res.values()))
+
+    # ------------------------------------------------------------------------------- rendering
+    def render_rays(self, rays_o, rays_d, near, far, ray0=0, need_weights=False, u_coarse=None, u_fine=None,
+                    keep_coarse=True):
+        """Ray-march an arbitrary number of device-resident rays in chunks of `render_chunk`. Returns
+        (dict_CM, dict_FM) of device tensors concatenated over chunks."""
+        N = rays_o.shape[0]
+        outs_c, outs_f = [], []
+        for s0 in range(0, max(N, 1), self.render_chunk):
+            s1 = min(N, s0 + self.render_chunk)
+            if s1 <= s0:
+                break
+            uc = None if u_coarse is None else u_coarse[s0:s1].contiguous()
+            uf = None if u_fine is None else u_fine[s0:s1].contiguous()
+            pc, pf = self.forward(rays_o[s0:s1], rays_d[s0:s1], near[s0:s1], far[s0:s1], uc, uf, ray0 + s0,
+                                  need_weights=need_weights)
+            if not need_weights:
+                pc.pop("weights", None)
+            if keep_coarse:
+                outs_c.append(pc)
+            outs_f.append(pf)
+        cat = lambda ds: {k: torch.cat([d[k] for d in ds], dim=0) for k in ds[0]} if ds else {}
+        return cat(outs_c), cat(outs_f)
+
+    def predict(self, x=None, return_weights=True, as_numpy=True, **_):
+        """Model.predict over a render dataset (main/eval.py:48, main/render.py:85): returns
+        (dict_CM, dict_FM) with keys acc_map [N], weights [N,S], pred_rgb [N,3], pred_depth [N],
+        concatenated over the dataset's batches, as NumPy arrays like Keras does. Batches are
+        grouped into super-chunks of `render_chunk` rays before they hit the GPU (rays are
+        independent, so the result does not depend on the grouping). `return_weights=False` drops
+        the per-sample `weights` tensors (0.66 GB per 800x800 view that no reference consumer reads)."""
+        group, count = [], 0
+        res_c, res_f = [], []
+        ray0 = 0
+
+        def flush():
+            nonlocal group, count, ray0
+            if not group:
+                return
+            cols = list(zip(*group))
+            dev = []
+            for col in cols:
+                if isinstance(col[0], torch.Tensor) and col[0].is_cuda:
+                    dev.append(torch.cat(col, dim=0) if len(col) > 1 else col[0])
+                else:
+                    host = np.concatenate([np.asarray(c, dtype=np.float32) for c in col], axis=0)
+                    pin = torch.from_numpy(host).pin_memory()
+                    dev.append(pin.to(self.device, non_blocking=True))
+            pc, pf = self.render_rays(dev[0], dev[1], dev[2], dev[3], ray0, need_weights=return_weights)
+            res_c.append(pc)
+            res_f.append(pf)
+            ray0 += count
+            group, count = [], 0
+
+        for batch in x:
+            inp = batch[0]
+            group.append(inp)
+            count += int(inp[0].shape[0])
+            if count >= self.render_chunk:
+                flush()
+        flush()
+
+        def finish(ds):
+            if not ds:
+                return {}
+            out = {k: torch.cat([d[k] for d in ds], dim=0) for k in ds[0]}
+            if as_numpy:
+                out = {k: v.cpu().numpy() for k, v in out.items()}
+            return out
+
+        return finish(res_c), finish(res_f)
+
+
+def get_coarse_or_fine_model(model_name, num_units=256, params=None, **kw):
+    """get_coarse_or_fine_model (core/model.py:334-394): returns the named sub-model of a fresh NeRF."""
+    assert model_name in ("coarse", "fine")
+    assert num_units == 256, "the reference hard-codes 256 units (core/model.py:334)"
+    from .params import make_params
+    nerf = NeRF(params or make_params(), **kw)
+    return nerf.coarse_model if model_name == "coarse" else nerf.fine_model
+
+
+def setup_model(params, **kw):
+    """setup_model (core/model.py:396-432): Adam(ExponentialDecay(5e-4, 500000, 0.1)) + PSNRMetric."""
+    nerf = NeRF(params=params, **kw)
+    nerf.compile(optimizer="adam", metrics=[ops.PSNRMetric()],
+                 run_eagerly=getattr(params.system, "run_eagerly", False))
+    return nerf

@@ -1,0 +1,62 @@
+"""CPU: host-side logic of the package (dataset batching, params, PSNR, init, scene)."""
+import numpy as np
+import torch
+
+import nerf_tf2_b200 as nb
+from nerf_tf2_b200 import model as pm, scene as ps
+from oracle import model as om, ray_march as rm, scene as osc
+
+
+def test_glorot_init_matches_oracle_init():
+    flat = pm.glorot_uniform_params(7)
+    w = om.init_weights(7)
+    cat = np.concatenate([w[n].reshape(-1) for n in om.all_variable_names()])
+    assert np.array_equal(flat, cat)
+    assert pm.variable_names("coarse") == om.variable_names("coarse")
+
+
+def test_scene_matches_oracle_scene():
+    sc = ps.SyntheticScene(10, 12, num_cameras=8)
+    for i in (0, 3, 7):
+        v = osc.synthetic_view(10, 12, view=i)
+        assert np.allclose(sc.poses[i], v["c2w"], atol=1e-12)
+        assert np.array_equal(sc.K, v["K"])
+        assert np.float32(sc.near) == v["near"][0, 0] and np.float32(sc.far) == v["far"][0, 0]
+    assert np.allclose(ps.spherical_poses(4.0, 40.0, 8), rm.create_spherical_path(4.0, 40.0, 8), atol=1e-12)
+
+
+def test_ray_dataset_batching_semantics():
+    n = 10
+    a = [np.arange(n * k, dtype=np.float32).reshape(n, k) for k in (3, 3, 1, 1)]
+    ds = nb.RayDataset.from_tensor_slices((tuple(a),)).batch(4, drop_remainder=False)
+    batches = list(ds)
+    assert [b[0][0].shape[0] for b in batches] == [4, 4, 2] and len(ds) == 3
+    assert len(batches[0]) == 1 and len(batches[0][0]) == 4          # ((ro, rd, near, far),)
+    ds2 = nb.RayDataset.from_tensor_slices((tuple(a), (a[0],))).batch(4, drop_remainder=True)
+    b2 = list(ds2)
+    assert len(b2) == 2 and len(b2[0]) == 2 and b2[0][1][0].shape == (4, 3)
+    # repeat + shuffle: every epoch is a permutation, batches stay full
+    ds3 = nb.RayDataset.from_tensor_slices((tuple(a), (a[0],))).shuffle(seed=1).repeat().batch(5, drop_remainder=True)
+    it = iter(ds3)
+    seen = np.concatenate([next(it)[0][2][:, 0] for _ in range(2)])
+    assert sorted(seen.tolist()) == list(range(n))
+
+
+def test_params_defaults_and_overrides():
+    p = nb.make_params({"system": {"white_bg": True}}, N_fine=256)
+    assert p.system.white_bg is True and p.sampling.N_fine == 256 and p.sampling.N_coarse == 64
+    assert p.data.batch_size == 4096 and p.sampling.lin_inv_depth is True
+
+
+def test_psnr_functions():
+    rng = np.random.default_rng(0)
+    y, p = rng.random((64, 3), dtype=np.float32), rng.random((64, 3), dtype=np.float32)
+    m = nb.PSNRMetric()
+    m.update_state(torch.from_numpy(y[:32]), torch.from_numpy(p[:32]))
+    m.update_state(torch.from_numpy(y[32:]), torch.from_numpy(p[32:]))
+    o = rm.PSNRMetric(); o.update_state(y, p)
+    assert abs(m.result() - float(o.result())) < 1e-4
+    assert abs(nb.psnr_metric_numpy(y, p) - rm.psnr_metric_numpy(y, p)) < 1e-12
+    assert abs(float(nb.psnr_metric(torch.from_numpy(y), torch.from_numpy(p))) - rm.psnr_metric_numpy(y, p)) < 1e-4
+    m.reset_states()
+    assert m.state.sum() == 0
