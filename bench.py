@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the NeRF ray-march hot path (BASELINE.json `metric`:
+rendered rays/s, 64+128 samples, 800x800).
+
+  python bench.py --gpus N --steps K --warmup W            (this repo's sm_100a path)
+  python bench.py --impl reference --gpus N --steps K ...   (the reference's CPU path: the oracle
+                                                             port, TensorFlow is not installable)
+
+A "step" is one full 800x800 view (640 000 rays, 157 reference chunks' worth of work) marched
+through coarse + fine networks. With N > 1 (torchrun, one rank per GPU) every rank renders its own
+view of the synthetic 360-degree scene -- views are independent units, no data-path collective --
+so scaling is "weak" and `value` is the whole-job aggregate.
+
+One JSON line is printed by rank 0. Besides the contract keys it carries
+  roofline      dominant kernel (fused encoding+MLP, tensor bound): algorithmic FLOPs / CUDA-event time
+  roofline_hbm  the integrator and the hierarchical sampler against measured HBM bandwidth
+  cpu_baseline  the oracle timed on the host cores on a bounded sample (rank 0, N=1)
+  e2e           the same metric through NeRF.predict() with HOST rays (H2D + D2H inside the timing)
+  train         4096-ray coarse+fine train steps/s (secondary metric of BASELINE.json)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 800
+N_COARSE, N_FINE = 64, 128
+FLOP_PER_ROW = 1186816                      # 2 x 593 408 MAC, unpadded
+ROWS_PER_RAY = N_COARSE + (N_COARSE + N_FINE)
+REF_SAMPLE_RAYS = 1024                      # bounded sample per step for the CPU arm
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_rays_per_s(sample_rays, seed=0):
+    """The reference arithmetic on the host cores: oracle forward (random uniforms fixed by seed)."""
+    import torch
+    from oracle import model as om, scene as osc
+    torch.set_num_threads(os.cpu_count())
+    v = osc.synthetic_view(H, W, view=0)
+    rng = np.random.default_rng(seed)
+    sel = rng.choice(H * W, size=sample_rays, replace=False)
+    w = om.init_weights(0)
+    uc = rng.random((sample_rays, N_COARSE), dtype=np.float32)
+    uf = rng.random((sample_rays, N_FINE), dtype=np.float32)
+    t0 = time.time()
+    om.forward(w, v["rays_o"][sel], v["rays_d"][sel], v["near"][sel], v["far"][sel], N_COARSE, N_FINE,
+               lin_inv_depth=True, perturb=True, white_bg=True, u_coarse=uc, u_fine=uf)
+    dt = time.time() - t0
+    return sample_rays / dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for i in range(args.warmup):
+        oracle_rays_per_s(REF_SAMPLE_RAYS, seed=i)
+    t0 = time.time()
+    cores = 1
+    for i in range(args.steps):
+        _, cores = oracle_rays_per_s(REF_SAMPLE_RAYS, seed=100 + i)
+    dt = time.time() - t0
+    val = REF_SAMPLE_RAYS * args.steps / dt
+    sample = f"{REF_SAMPLE_RAYS} random rays of the 800x800 view per step, coarse+fine 64+128, fp32 torch-CPU/NumPy oracle"
+    line = {"impl": "reference", "metric": "rendered rays/s (64+128 samples, 800x800)", "value": val, "unit": "rays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: synthetic lego-shaped 800x800 view, 64+128 samples (bounded sample)"},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+class KernelTimer:
+    """CUDA-event brackets around the C-ABI launches, on the launching (current) stream."""
+
+    def __init__(self, torch):
+        self.torch, self.ev = torch, {}
+
+    def wrap(self, name, fn):
+        def inner(*a, **k):
+            e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            self.ev.setdefault(name, []).append((e0, e1, a, k))
+            return out
+        return inner
+
+    def totals(self):
+        return {n: (sum(e0.elapsed_time(e1) for e0, e1, _, _ in evs), len(evs)) for n, evs in self.ev.items()}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import nerf_tf2_b200 as nb
+    from nerf_tf2_b200 import ray_utils as ru, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pk = peaks()
+    params = nb.make_params({"system": {"white_bg": True}}, N_coarse=N_COARSE, N_fine=N_FINE, perturb=True, lin_inv_depth=True)
+    nerf = nb.setup_model(params, precision=args.precision, seed=0, rng_seed=1234, render_chunk=args.chunk)
+    scene = nb.scene.SyntheticScene(H, W, num_cameras=max(8, world))
+    view = rank % len(scene)
+    ds_dev = nb.create_dataset_for_render(H, W, scene.poses[view], scene.bounds, scene.K, batch_size=4096, on_device=True)
+    ro, rd, near, far = ds_dev.inputs
+    n_rays = ro.shape[0]
+
+    lib = _lib.load()
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        nerf.render_rays(ro, rd, near, far, need_weights=False)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs, kernel path only (+ per-kernel CUDA events)
+    kt = KernelTimer(torch)
+    orig = (nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse)
+    nerf._mlp = kt.wrap("mlp", nerf._mlp)
+    ru.post_process_model_output = kt.wrap("composite", ru.post_process_model_output)
+    ru.sample_fine = kt.wrap("sample_fine", ru.sample_fine)
+    ru.sample_coarse = kt.wrap("sample_coarse", ru.sample_coarse)
+    clocks = ClockSampler(local) if rank == 0 else None
+    barrier()
+    launches0 = lib.nerfb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        nerf.render_rays(ro, rd, near, far, need_weights=False)
+    e1.record()
+    barrier()
+    tw1 = time.time()
+    launches = lib.nerfb200_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        ms = nb.dist.max_over_ranks(ms, dev)
+    clk = clocks.stop(tw0, tw1) if clocks else None
+    nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse = orig
+    value = world * n_rays * args.steps / (ms / 1e3)
+
+    tot = kt.totals()
+    mlp_ms, mlp_n = tot["mlp"]
+    mlp_flop = args.steps * n_rays * ROWS_PER_RAY * FLOP_PER_ROW
+    mlp_tflops = mlp_flop / (mlp_ms / 1e3) / 1e12
+    comp_ms, comp_n = tot["composite"]
+    # coarse: 24*S+20 B/ray with the [B,S] weights store; fine in render mode skips it: 20*S+20
+    comp_bytes = args.steps * n_rays * ((24 * N_COARSE + 20) + (20 * (N_COARSE + N_FINE) + 20))
+    sf_ms, sf_n = tot["sample_fine"]
+    # weights 4Nc + bin edges 4(Nc+1) + t_coarse 4Nc read, t_sorted 4(Nc+Nf) written; u generated in-kernel
+    sf_bytes = args.steps * n_rays * (4 * N_COARSE * 2 + 4 * (N_COARSE + 1) + 4 * (N_COARSE + N_FINE))
+    roofline = {"bound": "tensor", "kernel": "mlp_tc_forward_kernel (fused encoding + 8x256 MLP, coarse and fine launches)",
+                "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
+                "peak_kind": f"bf16 sustained, {pk['source']}", "frac_of_burst": mlp_tflops / pk["tensor_burst"],
+                "traffic": None, "launches": mlp_n, "avg_launch_ms": mlp_ms / mlp_n,
+                "share_of_step": mlp_ms / ms}
+    roofline_hbm = [
+        {"kernel": "composite_fwd_kernel", "bound": "hbm", "achieved": comp_bytes / (comp_ms / 1e3) / 1e9, "peak": pk["hbm"],
+         "unit": "GB/s", "frac": comp_bytes / (comp_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": comp_n,
+         "share_of_step": comp_ms / ms},
+        {"kernel": "sample_fine_kernel", "bound": "hbm", "achieved": sf_bytes / (sf_ms / 1e3) / 1e9, "peak": pk["hbm"],
+         "unit": "GB/s", "frac": sf_bytes / (sf_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": sf_n,
+         "share_of_step": sf_ms / ms},
+    ]
+
+    # ---- timed region 2: end to end through NeRF.predict() with HOST rays (pinned), H2D + D2H included
+    e2e_val = None
+    if not args.no_e2e:
+        host = tuple(a.cpu().numpy() for a in (ro, rd, near, far))
+        ds_host = nb.RayDataset.from_tensor_slices((host,)).batch(4096, drop_remainder=False)
+        for _ in range(2):
+            nerf.predict(ds_host, return_weights=False)
+        barrier()
+        t0 = time.time()
+        for _ in range(args.steps):
+            nerf.predict(ds_host, return_weights=False)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        if world > 1:
+            dt = nb.dist.max_over_ranks(dt, dev)
+        e2e_val = world * n_rays * args.steps / dt
+    h2d = n_rays * (3 + 3 + 1 + 1) * 4
+    d2h = n_rays * (3 + 1 + 1) * 4 * 2
+
+    # ---- secondary metric: 4096-ray training step (coarse+fine fwd/bwd + Adam [+ all-reduce])
+    train = None
+    if not args.no_train:
+        try:
+            train = bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args)
+        except Exception as ex:  # report, do not hide
+            train = {"error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rps, cores = oracle_rays_per_s(2048)
+        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+               "sample": "2048 random rays of the same 800x800 view, coarse+fine 64+128, fp32 torch-CPU/NumPy oracle (TensorFlow not installable)"}
+
+    if rank == 0:
+        line = {"metric": "rendered rays/s (64+128 samples, 800x800)", "value": value, "unit": "rays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": "BASELINE.json configs[1]: synthetic lego-shaped 800x800 single-view render, 64+128 samples, "
+                                       "random-init coarse+fine 8x256 MLPs, white_bg, perturb on (in-kernel Philox)",
+                           "rays_per_step_per_gpu": n_rays, "render_chunk_rays": args.chunk,
+                           "l2": "inputs larger than L2 (per-chunk rgb/sigma/t buffers > 126 MB); no explicit flush",
+                           "parallelism": f"ray-sharded x{world} (one view per rank, no collective)"},
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "NeRF.predict(RayDataset of host NumPy rays, return_weights=False)"},
+                "gpu_launches": int(launches), "clocks": clk, "train": train}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
+    B = 4096
+    Bl = B // world
+    scene = nb.scene.SyntheticScene(H, W, num_cameras=8)
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    ids = torch.randint(0, H * W, (Bl,), generator=g, dtype=torch.int32).to(dev)
+    ro, rd = nb.ray_utils.get_rays_at(H, W, scene.K, scene.poses[0], ids)
+    near = torch.full((Bl, 1), scene.near, device=dev); far = torch.full((Bl, 1), scene.far, device=dev)
+    rgb = torch.rand((Bl, 3), device=dev)
+    p = nb.make_params({"system": {"white_bg": True}})
+    tn = nb.setup_model(p, precision=args.precision, train_precision=args.train_precision, seed=0)
+    if world > 1:
+        tn.set_distributed()
+    batch = ((ro, rd, near, far), (rgb,))
+    steps = max(2, min(args.steps, 10))
+    for _ in range(3):
+        tn.train_step(batch)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tn.train_step(batch)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        ms = nb.dist.max_over_ranks(ms, dev)
+    sps = steps / (ms / 1e3)
+    flop = 3489024 * B * ROWS_PER_RAY
+    return {"metric": "train steps/s (4096-ray batch, coarse+fine fwd/bwd + Adam, data-parallel all-reduce)",
+            "value": sps, "unit": "steps/s", "ms_per_step": ms / steps, "precision": args.train_precision,
+            "global_batch": B, "achieved_tflops": flop * sps / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--train-precision", default="fp32", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--chunk", type=int, default=65536, help="rays per internal render chunk")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,6 +55,9 @@ typedef struct nerfb200_ctx nerfb200_ctx;
 
 NERFB200_API const char* nerfb200_last_error(void);
 NERFB200_API int nerfb200_abi_version(void);
+/* Number of kernels this library has launched in the process (bench.py reports the delta over the
+ * timed region as `gpu_launches`). */
+NERFB200_API int64_t nerfb200_launch_count(void);
 
 /* Offsets (in floats) of the 24 variables of one model inside its flat parameter block,
  * order = model.trainable_variables (kernel, bias per layer). offsets[24] = total. */

@@ -24,6 +24,7 @@ _i64, _i32, _vp, _u64, _dbl = C.c_int64, C.c_int, C.c_void_p, C.c_uint64, C.c_do
 SIGNATURES = {
     "nerfb200_last_error": (C.c_char_p, []),
     "nerfb200_abi_version": (_i32, []),
+    "nerfb200_launch_count": (_i64, []),
     "nerfb200_param_offsets": (_i32, [C.POINTER(_i64)]),
     "nerfb200_get_rays": (_i32, [_i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _i64, _i64, _vp, _vp, _vp]),
     "nerfb200_get_rays_f32": (_i32, [_i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _i64, _i64, _vp, _vp, _vp]),

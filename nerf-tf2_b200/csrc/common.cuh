@@ -4,12 +4,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 
 #include "../../include/nerfb200.h"
 
 namespace nb {
 
 void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;   // kernels launched by this library (process-wide)
 
 #define NB_CHECK_ARG(cond, ...)                        \
     do {                                               \
@@ -29,7 +31,11 @@ void set_error(const char* fmt, ...);
         }                                                                              \
     } while (0)
 
-#define NB_LAUNCH_CHECK() NB_CUDA(cudaGetLastError())
+#define NB_LAUNCH_CHECK()                 \
+    do {                                  \
+        nb::g_launches.fetch_add(1);      \
+        NB_CUDA(cudaGetLastError());      \
+    } while (0)
 
 constexpr int kNumVars = NERFB200_NUM_VARS_PER_MODEL;
 constexpr int kParamsPerModel = NERFB200_PARAMS_PER_MODEL;

@@ -191,8 +191,8 @@ extern "C" {
 int nerfb200_composite_fwd(int64_t B, int S, const float* sigma, const float* rgb, const float* t_vals, int white_bg,
                            float* weights, float* pred_rgb, float* pred_depth, float* acc_map, void* stream) {
     NB_CHECK_ARG(B >= 0 && S >= 2 && S <= 1024, "composite_fwd: need 2 <= S <= 1024, got S=%d", S);
-    NB_CHECK_ARG(sigma && rgb && t_vals && pred_rgb && pred_depth && acc_map, "composite_fwd: NULL pointer");
     if (B == 0) return 0;
+    NB_CHECK_ARG(sigma && rgb && t_vals && pred_rgb && pred_depth && acc_map, "composite_fwd: NULL pointer");
     unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
     NB_DISPATCH_E(pick_E(S), (composite_fwd_kernel<E><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
                                  B, S, sigma, rgb, t_vals, white_bg, weights, pred_rgb, pred_depth, acc_map)));
@@ -203,8 +203,8 @@ int nerfb200_composite_fwd(int64_t B, int S, const float* sigma, const float* rg
 int nerfb200_composite_bwd(int64_t B, int S, const float* sigma, const float* rgb, const float* t_vals, int white_bg,
                            const float* d_pred_rgb, float* d_sigma, float* d_rgb, void* stream) {
     NB_CHECK_ARG(B >= 0 && S >= 2 && S <= 1024, "composite_bwd: need 2 <= S <= 1024, got S=%d", S);
-    NB_CHECK_ARG(sigma && rgb && t_vals && d_pred_rgb && d_sigma && d_rgb, "composite_bwd: NULL pointer");
     if (B == 0) return 0;
+    NB_CHECK_ARG(sigma && rgb && t_vals && d_pred_rgb && d_sigma && d_rgb, "composite_bwd: NULL pointer");
     unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
     NB_DISPATCH_E(pick_E(S), (composite_bwd_kernel<E><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
                                  B, S, sigma, rgb, t_vals, white_bg, d_pred_rgb, d_sigma, d_rgb)));

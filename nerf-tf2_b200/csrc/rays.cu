@@ -4,10 +4,12 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <atomic>
 
 namespace nb {
 
 static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -188,6 +190,7 @@ using namespace nb;
 extern "C" {
 
 const char* nerfb200_last_error(void) { return nb::g_err; }
+int64_t nerfb200_launch_count(void) { return (int64_t)nb::g_launches.load(); }
 int nerfb200_abi_version(void) { return NERFB200_ABI_VERSION; }
 
 int nerfb200_param_offsets(int64_t* offsets) {
@@ -241,8 +244,9 @@ int nerfb200_get_rays_at(int H, int W, const float* K, const float* c2w, const i
 int nerfb200_sample_coarse(int64_t B, int Nc, int lin_inv_depth, int perturb, const float* near, const float* far,
                            const float* u_coarse, uint64_t seed, int64_t ray0, float* t_vals, float* bin_edges,
                            void* stream) {
-    NB_CHECK_ARG(B >= 0 && Nc >= 2 && near && far && t_vals && bin_edges, "sample_coarse: bad arguments");
+    NB_CHECK_ARG(B >= 0 && Nc >= 2, "sample_coarse: bad shape");
     if (B == 0) return 0;
+    NB_CHECK_ARG(near && far && t_vals && bin_edges, "sample_coarse: NULL pointer");
     sample_coarse_kernel<<<blocks_for(B * (Nc + 1), 256), 256, 0, (cudaStream_t)stream>>>(
         B, Nc, lin_inv_depth, perturb, near, far, u_coarse, seed, ray0, t_vals, bin_edges);
     NB_LAUNCH_CHECK();
@@ -251,16 +255,18 @@ int nerfb200_sample_coarse(int64_t B, int Nc, int lin_inv_depth, int perturb, co
 
 int nerfb200_make_inputs(int64_t B, int S, const float* rays_o, const float* rays_d, const float* t_vals, float* xyz,
                          float* dirs, void* stream) {
-    NB_CHECK_ARG(B >= 0 && S > 0 && rays_o && rays_d && t_vals && xyz && dirs, "make_inputs: bad arguments");
+    NB_CHECK_ARG(B >= 0 && S > 0, "make_inputs: bad shape");
     if (B == 0) return 0;
+    NB_CHECK_ARG(rays_o && rays_d && t_vals && xyz && dirs, "make_inputs: NULL pointer");
     make_inputs_kernel<<<blocks_for(B * S, 256), 256, 0, (cudaStream_t)stream>>>(B * S, S, rays_o, rays_d, t_vals, xyz, dirs);
     NB_LAUNCH_CHECK();
     return 0;
 }
 
 int nerfb200_positional_encode(int64_t R, int L, const float* x, float* out, void* stream) {
-    NB_CHECK_ARG(R >= 0 && L >= 1 && L <= 16 && x && out, "positional_encode: bad arguments");
+    NB_CHECK_ARG(R >= 0 && L >= 1 && L <= 16, "positional_encode: bad shape");
     if (R == 0) return 0;
+    NB_CHECK_ARG(x && out, "positional_encode: NULL pointer");
     posenc_kernel<<<blocks_for(R * (3 + 6 * L), 256), 256, 0, (cudaStream_t)stream>>>(R, L, x, out);
     NB_LAUNCH_CHECK();
     return 0;

@@ -220,7 +220,7 @@ extern "C" {
 int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights, const float* bin_edges,
                          const float* t_coarse, const float* u_fine, uint64_t seed, int64_t ray0, float* t_sorted,
                          int32_t* piece_idxs, float* cdf, float* t_fine, void* stream) {
-    NB_CHECK_ARG(B >= 0 && bin_weights && bin_edges && t_coarse && t_sorted, "sample_fine: NULL pointer");
+    NB_CHECK_ARG(B >= 0, "sample_fine: negative ray count");
     if (!(Nc >= 32 && Nc <= 256 && Nc % 32 == 0)) {
         set_error("sample_fine: N_coarse must be a multiple of 32 in [32,256], got %d", Nc);
         return NERFB200_ENOTSUP;
@@ -230,6 +230,7 @@ int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights, co
         return NERFB200_ENOTSUP;
     }
     if (B == 0) return 0;
+    NB_CHECK_ARG(bin_weights && bin_edges && t_coarse && t_sorted, "sample_fine: NULL pointer");
     int S = Nc + Nf, P2 = 1;
     while (P2 < S) P2 <<= 1;
     size_t smem = (size_t)kSamplerWarps * ((Nc + 1) * 2 + Nc * 2 + Nf + P2) * sizeof(float);
