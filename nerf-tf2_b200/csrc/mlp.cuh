@@ -9,6 +9,7 @@ struct nerfb200_ctx {
     void* packed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [bf16|fp16][coarse|fine]
     float* head_params[2] = {nullptr, nullptr};                       // fp32 biases + sigma head per model
     bool packed_valid = false;
+    int replicas = 1;                                                 // identical copies of each packed image
 };
 
 namespace nb {
