@@ -325,7 +325,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
-    ap.add_argument("--train-precision", default="fp32", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--chunk", type=int, default=65536, help="rays per internal render chunk")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -7,6 +7,7 @@ struct nerfb200_ctx {
     int num_sms = 148;
     // tensor-core operand images, one per (precision, model): see mlp_tc.cu for the layout
     void* packed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [bf16|fp16][coarse|fine]
+    void* packed_bwd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // W^T images for backward-data
     float* head_params[2] = {nullptr, nullptr};                       // fp32 biases + sigma head per model
     bool packed_valid = false;
     int replicas = 1;                                                 // identical copies of each packed image
@@ -24,7 +25,10 @@ int ref_forward(cudaStream_t st, const float* P, int64_t B, int S, const float* 
 int ref_backward(cudaStream_t st, const float* P, int64_t B, int S, const float* d_rgb, const float* d_sigma,
                  float* G, void* workspace, void* stash);
 
-// mlp_tc.cu
+// mlp_tc.cu / mlp_tc_train.cu
+int tc_train_create(nerfb200_ctx* ctx);
+void tc_train_destroy(nerfb200_ctx* ctx);
+int tc_train_pack(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st);
 int tc_create(nerfb200_ctx* ctx);
 void tc_destroy(nerfb200_ctx* ctx);
 int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st);

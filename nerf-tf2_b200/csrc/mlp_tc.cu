@@ -26,9 +26,9 @@
 // Shared memory (bytes): 2 x 64 KB activations, 2 x 16 KB encodings, 4 x 16 KB weight ring, barriers.
 #include "common.cuh"
 #include "mlp.cuh"
+#include "tc_common.cuh"
+#include "tc_layout.cuh"
 
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace nb {
@@ -175,101 +175,6 @@ __global__ void pack_heads_kernel(const float* __restrict__ P, float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must trap (reported as a CUDA error), never hang the GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
-            printf("nerfb200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-// tcgen05.wait::ld with the destination registers as in/out operands, so that no use of them can be
-// scheduled above the wait.
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :: "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (SBO), version 1.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D=f32, A/B = fmt (0 fp16, 1 bf16), both K-major, M=128.
-__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int N) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-template <bool kHalf> __device__ __forceinline__ uint32_t pack2(float a, float b) {
-    if constexpr (kHalf) {
-        __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
-    } else {
-        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-constexpr int kTileRows = 128;
 constexpr int kActBytes = 4 * 16384;    // 128 rows x 256 K x 2 B, four K chunks of [128 x 64]
 constexpr int kEncBytes = 16384;        // 128 rows x 64 K x 2 B
 constexpr int kStageBytes = 16384;      // [128 N x 64 K]
@@ -294,14 +199,11 @@ struct TcParams {
     const float* heads;      // HeadOffsets block
     const float* ro; const float* rd; const float* t;
     float* rgb; float* sigma;
+    uint8_t* stash;          // training: per-tile activation stash (tc_layout.cuh), else NULL
     int64_t R;               // rows
     int S;
     int num_tiles;
 };
-
-// byte offset of (row, 16-byte unit) inside a [128 x 64] swizzled chunk
-__device__ __forceinline__ uint32_t swz(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
-
 
 struct RowCtx {
     int64_t grow;
@@ -384,7 +286,7 @@ __device__ __forceinline__ void write_enc_dir(const float (&dir)[3], uint8_t* en
 // -> + bias (smem broadcast) -> ReLU -> 16-bit -> swizzled smem = next layer's A operand.
 template <bool kHalf, int NG, bool kRelu, bool kSigma>
 __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_bias, uint8_t* act, int row,
-                                              const float4* ws4, float& sig_acc) {
+                                              const float4* ws4, float& sig_acc, uint32_t* mask_row = nullptr) {
     uint32_t r[2][32];
     tmem_ld32(tmem_row, r[0]);
 #pragma unroll
@@ -405,6 +307,12 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_
         if (kRelu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            if (mask_row) {   // training: ReLU bitmask of this group for the backward pass
+                uint32_t m = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f) ? (1u << i) : 0u;
+                mask_row[g] = m;
+            }
         }
         if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
 #pragma unroll
@@ -431,19 +339,10 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_
 }
 
 
-// 64-bit UMMA descriptor from its low word (start address >> 4; LBO = 0): the high word is constant
-// (SBO = 1024 B, version 1, SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
-    constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    uint64_t d;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
-    return d;
-}
-
 #define NB_T0() long long _t0 = dbg_on ? clock64() : 0
 #define NB_T1(slot) do { if (dbg_on) dbg_acc##slot += (unsigned long long)(clock64() - _t0); } while (0)
 
-template <bool kHalf>
+template <bool kHalf, bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcParams p) {
     const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
     unsigned long long dbg_acc0 = 0, dbg_acc1 = 0, dbg_acc2 = 0, dbg_acc3 = 0;
@@ -565,24 +464,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
         const float4* ws4 = reinterpret_cast<const float4*>(p.heads + HeadOffsets::wsigma);
 
         RowCtx cur, nxt;
+        // training: activation images leave through bulk stores issued by one thread per slot; a store is
+        // queued when its source (activation buffer / encoding buffer) has been written and is issued at
+        // the next job boundary, after the slot's barrier has made all 128 threads' writes visible
+        uint8_t* pendA_dst = nullptr; uint32_t pendA_bytes = 0;
+        uint8_t* pendE_dst = nullptr; uint32_t pendE_bytes = 0;
+        const uint32_t act_saddr = sbase + kSmemAct + t * kActBytes, enc_saddr = sbase + kSmemEnc + t * kEncBytes;
         int pr = blockIdx.x;
-        if (pr < pairs && pr * 2 + t < p.num_tiles) prep_tile<kHalf>(p, pr * 2 + t, row, enc, cur);
+        if (pr < pairs && pr * 2 + t < p.num_tiles) {
+            prep_tile<kHalf>(p, pr * 2 + t, row, enc, cur);
+            if (kTrain) { pendE_dst = p.stash + (size_t)(pr * 2 + t) * kStashTileBytes + kStashChunkEncXyz * 16384; pendE_bytes = 16384; }
+        }
         for (; pr < pairs; pr += gridDim.x) {
             const int tile = pr * 2 + t;
             if (tile >= p.num_tiles) continue;
+            uint8_t* tstash = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
             mbar_arrive(act_ready(t));                 // enc_xyz of this tile is in place (prep_tile fenced)
 
             float sig_acc = 0.f;
             for (int j = 0; j < kNumJobs; ++j) {
                 // stage this job's biases in shared memory while the tensor core works
                 long long _tb = dbg_on ? clock64() : 0;
-                named_bar_sync(1 + t, kTileRows);      // all 4 warps are done with the previous biases
+                named_bar_sync(1 + t, kTileRows);      // all 4 warps are done with the previous job (and its biases)
+                bool issued = false;
+                if (kTrain && row == 0) {
+                    if (pendA_bytes) { bulk_s2g(pendA_dst, act_saddr, pendA_bytes); issued = true; }
+                    if (pendE_bytes) { bulk_s2g(pendE_dst, enc_saddr, pendE_bytes); issued = true; }
+                    if (issued) bulk_commit_group();
+                }
+                pendA_bytes = 0; pendE_bytes = 0;
                 {
                     const int N = j < 9 ? 256 : (j == 9 ? 128 : 16);
                     const float* b = p.heads + HeadOffsets::bias(j);
                     if (row < N) s_bias[row] = __ldg(b + row);
                     if (row + 128 < N) s_bias[row + 128] = __ldg(b + row + 128);
                 }
+                if (kTrain && issued) bulk_wait_read_all();   // the sources may be overwritten after the next barrier
                 named_bar_sync(1 + t, kTileRows);
                 if (dbg_on) dbg_acc2 += (unsigned long long)(clock64() - _tb);
                 { NB_T0(); mbar_wait(acc_full(t), acc_phase); NB_T1(0); }
@@ -594,14 +511,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
                     fence_proxy_async();
                     mbar_arrive(act_ready(t));
                 } else if (j < 10) {
-                    if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc);
+                    uint32_t* mrow = nullptr;
+                    if (kTrain && j != 8)
+                        mrow = reinterpret_cast<uint32_t*>(tstash + kStashMaskOfs) + ((j == 9 ? 8 : j) * 128 + row) * 8;
+                    if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
                     else if (j == 8) epilogue_cols<kHalf, 8, false, false>(tmem_row, s_bias, act, row, ws4, sig_acc);
-                    else if (j == 9) epilogue_cols<kHalf, 4, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc);
-                    else epilogue_cols<kHalf, 8, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc);
-                    if (j == 5) write_enc_dir<kHalf>(cur.dir, enc, row);   // dense_5 has consumed enc_xyz
-                    if (j == 7 && cur.valid) {
-                        float sg = sig_acc + __ldg(p.heads + HeadOffsets::bsigma);
-                        p.sigma[cur.grow] = fmaxf(sg, 0.f);
+                    else if (j == 9) epilogue_cols<kHalf, 4, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
+                    else epilogue_cols<kHalf, 8, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
+                    if (kTrain) {
+                        pendA_dst = tstash + (j < 8 ? stash_chunk_Y(j) : j == 8 ? kStashChunkBott : kStashChunkY9) * 16384;
+                        pendA_bytes = j == 9 ? 2 * 16384 : 4 * 16384;
+                    }
+                    if (j == 5) {
+                        write_enc_dir<kHalf>(cur.dir, enc, row);   // dense_5 has consumed enc_xyz
+                        if (kTrain) { pendE_dst = tstash + kStashChunkEncDir * 16384; pendE_bytes = 16384; }
+                    }
+                    if (j == 7) {
+                        float sg = fmaxf(sig_acc + __ldg(p.heads + HeadOffsets::bsigma), 0.f);
+                        if (cur.valid) p.sigma[cur.grow] = sg;
+                        if (kTrain) reinterpret_cast<float*>(tstash + kStashOutOfs)[3 * 128 + row] = cur.valid ? sg : 0.f;
                     }
                     tc_fence_before();
                     fence_proxy_async();
@@ -611,7 +539,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
                         // dense_9 has consumed enc_dir: encode the NEXT tile of this slot now, off the critical path
                         const int npr = pr + gridDim.x;
                         NB_T0();
-                        if (npr < pairs && npr * 2 + t < p.num_tiles) prep_tile<kHalf>(p, npr * 2 + t, row, enc, nxt);
+                        if (npr < pairs && npr * 2 + t < p.num_tiles) {
+                            prep_tile<kHalf>(p, npr * 2 + t, row, enc, nxt);
+                            if (kTrain) { pendE_dst = p.stash + (size_t)(npr * 2 + t) * kStashTileBytes + kStashChunkEncXyz * 16384; pendE_bytes = 16384; }
+                        }
                         NB_T1(3);
                     }
                 } else {
@@ -619,17 +550,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
                     uint32_t r[32];
                     tmem_ld32(tmem_row, r);   // columns 16..31 hold stale data from dense_9; ignored
                     tmem_ld_wait(r);
-                    if (cur.valid) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            float x = __uint_as_float(r[c]) + s_bias[c];
-                            p.rgb[3 * cur.grow + c] = 1.f / (1.f + expf(-x));
-                        }
+                    for (int c = 0; c < 3; ++c) {
+                        float x = __uint_as_float(r[c]) + s_bias[c];
+                        float y = 1.f / (1.f + expf(-x));
+                        if (cur.valid) p.rgb[3 * cur.grow + c] = y;
+                        if (kTrain) reinterpret_cast<float*>(tstash + kStashOutOfs)[3 * row + c] = cur.valid ? y : 0.f;
                     }
                     tc_fence_before();
                 }
             }
             cur = nxt;
+        }
+        if (kTrain) {
+            // flush what the last job queued, and do not exit while bulk stores are in flight
+            named_bar_sync(1 + t, kTileRows);
+            if (row == 0) {
+                if (pendA_bytes) bulk_s2g(pendA_dst, act_saddr, pendA_bytes);
+                if (pendE_bytes) bulk_s2g(pendE_dst, enc_saddr, pendE_bytes);
+                bulk_commit_group();
+                bulk_wait_all();
+            }
         }
     }
 
@@ -670,12 +611,15 @@ int tc_create(nerfb200_ctx* ctx) {
     for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc((void**)&ctx->head_params[m], HeadOffsets::total * sizeof(float)));
     int rc = upload_table();
     if (rc) return rc;
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    return 0;
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    return tc_train_create(ctx);
 }
 
 void tc_destroy(nerfb200_ctx* ctx) {
+    tc_train_destroy(ctx);
     for (int pz = 0; pz < 2; ++pz)
         for (int m = 0; m < 2; ++m) if (ctx->packed[pz][m]) cudaFree(ctx->packed[pz][m]);
     for (int m = 0; m < 2; ++m) if (ctx->head_params[m]) cudaFree(ctx->head_params[m]);
@@ -695,18 +639,16 @@ int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st
         pack_heads_kernel<<<(HeadOffsets::total + 255) / 256, 256, 0, st>>>(P, ctx->head_params[m]);
     }
     NB_LAUNCH_CHECK();
+    int rc = tc_train_pack(ctx, flat_params, st);
+    if (rc) return rc;
     ctx->packed_valid = true;
     return 0;
 }
-
-int64_t tc_workspace_bytes(int64_t, int) { return 0; }
-int64_t tc_stash_bytes(int64_t) { return 0; }
 
 int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
                float* rgb, float* sigma, void* workspace, void* stash, cudaStream_t st) {
     (void)workspace;
     if (!ctx->packed_valid) { set_error("mlp_forward: pack_weights has not been called"); return NERFB200_ESTATE; }
-    if (stash) { set_error("mlp_forward: training stash is not supported by the tensor-core path yet"); return NERFB200_ENOTSUP; }
     const int64_t R = B * S;
     if (R == 0) return 0;
     NB_CHECK_ARG((R + kTileRows - 1) / kTileRows < (int64_t)1 << 30, "mlp_forward: too many rows");
@@ -716,6 +658,7 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
     p.replicas = ctx->replicas;
     p.heads = ctx->head_params[which];
     p.ro = ro; p.rd = rd; p.t = t; p.rgb = rgb; p.sigma = sigma; p.R = R; p.S = S;
+    p.stash = (uint8_t*)stash;
     p.num_tiles = (int)((R + kTileRows - 1) / kTileRows);
     int pairs = (p.num_tiles + 1) / 2;
     int grid = pairs < ctx->num_sms ? pairs : ctx->num_sms;
@@ -726,8 +669,13 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
         NB_CUDA(cudaMalloc((void**)&p.dbg, 32 * sizeof(unsigned long long)));
         NB_CUDA(cudaMemsetAsync(p.dbg, 0, 32 * sizeof(unsigned long long), st));
     }
-    if (half) mlp_tc_forward_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(p);
-    else mlp_tc_forward_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(p);
+    if (stash) {
+        if (half) mlp_tc_forward_kernel<true, true><<<grid, kThreads, kSmemTotal, st>>>(p);
+        else mlp_tc_forward_kernel<false, true><<<grid, kThreads, kSmemTotal, st>>>(p);
+    } else {
+        if (half) mlp_tc_forward_kernel<true, false><<<grid, kThreads, kSmemTotal, st>>>(p);
+        else mlp_tc_forward_kernel<false, false><<<grid, kThreads, kSmemTotal, st>>>(p);
+    }
     NB_LAUNCH_CHECK();
     if (debug) {
         unsigned long long h[32];
@@ -741,12 +689,6 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
                     h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
     }
     return 0;
-}
-
-int tc_backward(nerfb200_ctx*, int, int, int64_t, int, const float*, const float*, const float*, const float*,
-                const float*, const float*, float*, void*, void*, cudaStream_t) {
-    set_error("mlp_backward: tensor-core backward not implemented yet; use NERFB200_FP32");
-    return NERFB200_ENOTSUP;
 }
 
 }  // namespace nb

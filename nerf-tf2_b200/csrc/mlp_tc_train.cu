@@ -1,0 +1,654 @@
+// Backward of the 8x256 MLP (tf.GradientTape over core/model.py:148-170) on the tensor cores.
+//
+// Three kernels per model and step, all tcgen05.mma with fp32 accumulation in TMEM and 16-bit operands:
+//
+//  1. bwd_data_kernel  -- per 128-row tile, the chain dZ_9 -> dZ_8 -> ... -> dZ_0 stays on chip like the
+//     forward: dX = dZ . W^T (W^T streamed through the bulk-TMA ring), the epilogue applies the ReLU
+//     bitmask stashed by the training forward and writes dZ_{l-1} as the next A operand. The rgb and
+//     sigma heads (N = 3 and 1) are fp32 CUDA-core work in the prologue/epilogue. Every dZ_l leaves as
+//     a chunk image (tc_layout.cuh) for kernel 2. No dX for the network inputs: sample positions are
+//     constants for autodiff (stop_gradient, utils/ray_utils.py:377).
+//  2. dw_kernel        -- dW_l = X_l^T . dZ_l, a reduction over ALL rows: each CTA walks its share of the
+//     tiles, bulk-loads the X_l and dZ_l chunk images and feeds them to the tensor core as MN-major
+//     operands (K = rows); the [K_in x N_out] fp32 accumulator lives in TMEM for the whole pass and is
+//     flushed once per CTA. Bias gradients (column sums of dZ_l) are accumulated by the otherwise idle
+//     warps from the same shared-memory tiles.
+//  3. reduce_grads_kernel -- sums the per-CTA partials into the flat fp32 gradient buffer (Keras kernel
+//     layout [in,out]).
+#include "common.cuh"
+#include "mlp.cuh"
+#include "tc_common.cuh"
+#include "tc_layout.cuh"
+
+namespace nb {
+
+// =============================================================================================
+// W^T image for backward-data: chunks [128 in-features x 64 out-features], K-major (K = out features).
+// Jobs: B1 = dense_9 (bott part, K = 128), B2 = dense_8, B3..B9 = dense_7..dense_1 (dense_5: h4 part).
+constexpr int kBwdJobs = 9;
+struct BwdChunk { uint32_t gofs; uint8_t layer, nh, kc, pad; };
+constexpr int kBwdMaxChunks = 72;
+struct BwdTable { BwdChunk c[kBwdMaxChunks]; int n; int job_begin[kBwdJobs + 1]; uint32_t bytes; };
+
+static BwdTable build_bwd_table() {
+    BwdTable t{};
+    const int layers[kBwdJobs] = {L9, L8, L7, L6, L5, L4, L3, L2, L1};
+    uint32_t ofs = 0;
+    int n = 0;
+    for (int j = 0; j < kBwdJobs; ++j) {
+        t.job_begin[j] = n;
+        const int KC = j == 0 ? 2 : 4;
+        for (int nh = 0; nh < 2; ++nh)
+            for (int kc = 0; kc < KC; ++kc) {
+                t.c[n++] = BwdChunk{ofs, (uint8_t)layers[j], (uint8_t)nh, (uint8_t)kc, 0};
+                ofs += kChunkBytes;
+            }
+    }
+    t.job_begin[kBwdJobs] = n;
+    t.n = n;
+    t.bytes = ofs;
+    return t;
+}
+static const BwdTable& bwd_table() { static BwdTable t = build_bwd_table(); return t; }
+
+__constant__ BwdChunk c_bwd_chunks[kBwdMaxChunks];
+__constant__ int c_bwd_job_begin[kBwdJobs + 1];
+
+template <typename T> __device__ __forceinline__ T cvt16(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 cvt16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half cvt16<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T>
+__global__ void pack_bwd_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ img, int nchunks) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= (int64_t)nchunks * (kChunkBytes / 16)) return;
+    const int ci = (int)(u / (kChunkBytes / 16));
+    const BwdChunk ch = c_bwd_chunks[ci];
+    const uint32_t local = (uint32_t)(u % (kChunkBytes / 16)) * 16;
+    const int row = local >> 7, unit = ((local >> 4) & 7) ^ (row & 7);
+    const LayerDim dim = layer_dim(ch.layer);
+    const float* W = P + kernel_offset(ch.layer);
+    const int n = ch.nh * 128 + row;           // in-feature (row of the Keras kernel)
+    T vals[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = ch.kc * 64 + unit * 8 + e;   // out-feature (column of the Keras kernel)
+        float v = (n < dim.fan_in && k < dim.fan_out) ? W[(int64_t)n * dim.fan_out + k] : 0.f;
+        vals[e] = cvt16<T>(v);
+    }
+    *reinterpret_cast<uint4*>(img + ch.gofs + local) = *reinterpret_cast<uint4*>(vals);
+}
+
+// =============================================================================================
+// 1. backward-data kernel
+constexpr int kBStages = 4;
+constexpr int kBSmemAct = 0;                                   // 2 x 64 KB: dZ of the current layer (A operand)
+constexpr int kBSmemHead = kBSmemAct + 2 * 4 * kChunkBytes;    // 2 x 16 KB: head chunk (dZ_rgb, dZ_sigma)
+constexpr int kBSmemRing = kBSmemHead + 2 * kChunkBytes;       // 4 x 16 KB: W^T ring
+constexpr int kBSmemBar = kBSmemRing + kBStages * kChunkBytes;
+constexpr int kBSmemWsig = kBSmemBar + 256;                    // 256 fp32: sigma kernel
+constexpr int kBSmemTotal = kBSmemWsig + 1024;
+static_assert(kBSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+constexpr int kBThreads = 320;
+constexpr int kBProducerWarp = 8, kBMmaWarp = 9;
+
+struct BwdParams {
+    const uint8_t* wimg; uint32_t wimg_stride; int replicas;
+    const float* P;              // fp32 master parameters of this model (rgb / sigma heads)
+    const uint8_t* stash;        // activation stash of the training forward
+    uint8_t* gstash;             // out: gradient stash
+    const float* d_rgb; const float* d_sigma;
+    int64_t R; int num_tiles;
+};
+
+// One backward layer's epilogue for this thread's row: dZ_prev = (acc [+ dzs*wsig]) masked by the ReLU bitmask.
+template <bool kHalf, bool kMask, bool kSigma>
+__device__ __forceinline__ void bwd_epilogue_cols(uint32_t tmem_row, uint8_t* act, int row, const uint32_t (&mask)[8],
+                                                  const float* s_wsig, float dzs, bool valid) {
+    uint32_t r[2][32];
+    tmem_ld32(tmem_row, r[0]);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        uint32_t (&rr)[32] = r[g & 1];
+        tmem_ld_wait(rr);
+        if (g + 1 < 8) tmem_ld32(tmem_row + (uint32_t)(32 * (g + 1)), r[(g + 1) & 1]);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        if (kSigma) {
+            const float4* w4 = reinterpret_cast<const float4*>(s_wsig + 32 * g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 w = w4[i];
+                v[4 * i + 0] = fmaf(dzs, w.x, v[4 * i + 0]);
+                v[4 * i + 1] = fmaf(dzs, w.y, v[4 * i + 1]);
+                v[4 * i + 2] = fmaf(dzs, w.z, v[4 * i + 2]);
+                v[4 * i + 3] = fmaf(dzs, w.w, v[4 * i + 3]);
+            }
+        }
+        if (kMask) {
+            const uint32_t m = valid ? mask[g] : 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (m >> i) & 1u ? v[i] : 0.f;
+        } else if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        uint8_t* chunk = act + (g >> 1) * kChunkBytes;
+        const int u0 = (g & 1) * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint4 o;
+            o.x = pack2<kHalf>(v[8 * u + 0], v[8 * u + 1]);
+            o.y = pack2<kHalf>(v[8 * u + 2], v[8 * u + 3]);
+            o.z = pack2<kHalf>(v[8 * u + 4], v[8 * u + 5]);
+            o.w = pack2<kHalf>(v[8 * u + 6], v[8 * u + 7]);
+            *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = o;
+        }
+    }
+}
+
+template <bool kHalf>
+__global__ void __launch_bounds__(kBThreads, 1) bwd_data_kernel(const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbar = sbase + kBSmemBar;
+    // barriers: ring_full[4], ring_empty[4], act_ready[2], acc_full[2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kBSmemBar + 8 * (2 * kBStages + 4));
+    float* s_wsig = reinterpret_cast<float*>(smem + kBSmemWsig);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBStages; ++s) { mbar_init(sbar + 8 * s, 1); mbar_init(sbar + 8 * (kBStages + s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(sbar + 8 * (2 * kBStages + t), kTileRows); mbar_init(sbar + 8 * (2 * kBStages + 2 + t), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 256) s_wsig[threadIdx.x] = p.P[kernel_offset(LSIGMA) + threadIdx.x];
+    if (warp == kBMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int pairs = (p.num_tiles + 1) >> 1;
+    constexpr int fmt = kHalf ? 0 : 1;
+
+    if (warp == kBProducerWarp) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint8_t* wimg = p.wimg + (size_t)(blockIdx.x % p.replicas) * p.wimg_stride;
+            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x)
+                for (int j = 0; j < kBwdJobs; ++j)
+                    for (int t = 0; t < 2; ++t) {
+                        if (pr * 2 + t >= p.num_tiles) continue;
+                        for (int ci = c_bwd_job_begin[j]; ci < c_bwd_job_begin[j + 1]; ++ci) {
+                            mbar_wait(sbar + 8 * (kBStages + stage), phase ^ 1);
+                            mbar_expect_tx(sbar + 8 * stage, kChunkBytes);
+                            bulk_g2s(sbase + kBSmemRing + stage * kChunkBytes, wimg + c_bwd_chunks[ci].gofs, kChunkBytes, sbar + 8 * stage);
+                            if (++stage == kBStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+        }
+    } else if (warp == kBMmaWarp) {
+        if (lane == 0) {
+            const uint32_t ring_lo = ((sbase + kBSmemRing) >> 4) & 0x3FFFu;
+            constexpr uint32_t idesc = umma_idesc(fmt, 128);
+            uint32_t stage = 0, phase = 0, act_phase_bits = 0;
+            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+#pragma unroll 1
+                for (int j = 0; j < kBwdJobs; ++j) {
+                    const int KC = j == 0 ? 2 : 4;
+#pragma unroll 1
+                    for (int t = 0; t < 2; ++t) {
+                        if (pr * 2 + t >= p.num_tiles) continue;
+                        mbar_wait(sbar + 8 * (2 * kBStages + t), (act_phase_bits >> t) & 1u);
+                        act_phase_bits ^= 1u << t;
+                        tc_fence_after();
+                        const uint32_t act_lo = ((sbase + kBSmemAct + t * 4 * kChunkBytes) >> 4) & 0x3FFFu;
+                        const uint32_t d = tmem_base + (uint32_t)(t * 256);
+#pragma unroll 1
+                        for (int nh = 0; nh < 2; ++nh) {
+                            const uint32_t dd = d + (uint32_t)(nh * 128);
+#pragma unroll 1
+                            for (int kc = 0; kc < KC; ++kc) {
+                                mbar_wait(sbar + 8 * stage, phase);
+                                tc_fence_after();
+                                const uint32_t a_lo = act_lo + (uint32_t)(kc * 1024);
+                                const uint32_t b_lo = ring_lo + stage * (kChunkBytes >> 4);
+                                umma_f16(dd, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
+                                umma_f16(dd, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+                                umma_f16(dd, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+                                umma_f16(dd, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                                umma_commit(sbar + 8 * (kBStages + stage));
+                                if (++stage == kBStages) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                        umma_commit(sbar + 8 * (2 * kBStages + 2 + t));
+                    }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        const int t = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        uint8_t* act = smem + kBSmemAct + t * 4 * kChunkBytes;
+        uint8_t* head = smem + kBSmemHead + t * kChunkBytes;
+        const uint32_t act_saddr = sbase + kBSmemAct + t * 4 * kChunkBytes, head_saddr = sbase + kBSmemHead + t * kChunkBytes;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+        const uint32_t act_ready = sbar + 8 * (2 * kBStages + t), acc_full = sbar + 8 * (2 * kBStages + 2 + t);
+        uint32_t acc_phase = 0;
+        uint8_t* pend_dst = nullptr; uint32_t pend_bytes = 0; bool pend_head = false; uint8_t* pend_head_dst = nullptr;
+
+        for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
+            const int tile = pr * 2 + t;
+            if (tile >= p.num_tiles) continue;
+            const uint8_t* tstash = p.stash + (size_t)tile * kStashTileBytes;
+            uint8_t* gst = p.gstash + (size_t)tile * kGradTileBytes;
+            const int64_t grow = (int64_t)tile * kTileRows + row;
+            const bool valid = grow < p.R;
+            const float* outs = reinterpret_cast<const float*>(tstash + kStashOutOfs);
+
+            // ---- heads (fp32, CUDA cores): dZ_rgb = d_rgb * rgb(1-rgb); dZ_sigma = d_sigma * [sigma > 0]
+            float dzr[3] = {0.f, 0.f, 0.f}, dzs = 0.f;
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float y = outs[3 * row + c];
+                    dzr[c] = __ldg(p.d_rgb + 3 * grow + c) * y * (1.f - y);
+                }
+                dzs = outs[3 * 128 + row] > 0.f ? __ldg(p.d_sigma + grow) : 0.f;
+            }
+            // ---- everything below runs at a job boundary: wait until the previous tile's stores have read smem
+            named_bar_sync(1 + t, kTileRows);
+            bool issued = false;
+            if (row == 0) {
+                if (pend_bytes) { bulk_s2g(pend_dst, act_saddr, pend_bytes); issued = true; }
+                if (pend_head) { bulk_s2g(pend_head_dst, head_saddr, kChunkBytes); issued = true; }
+                if (issued) { bulk_commit_group(); bulk_wait_read_all(); }
+            }
+            pend_bytes = 0; pend_head = false;
+            named_bar_sync(1 + t, kTileRows);
+            // head chunk image: cols 0..2 = dZ_rgb, col 3 = dZ_sigma, rest 0
+            {
+                uint4 o = make_uint4(pack2<kHalf>(dzr[0], dzr[1]), pack2<kHalf>(dzr[2], dzs), 0u, 0u);
+                *reinterpret_cast<uint4*>(head + swz(row, 0)) = o;
+#pragma unroll
+                for (int u = 1; u < 8; ++u) *reinterpret_cast<uint4*>(head + swz(row, u)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            // dZ_9 = (dZ_rgb . Wrgb^T) masked by [Y9 > 0]  -> activation chunks 0,1 (128 columns)
+            {
+                const uint32_t* mrow = reinterpret_cast<const uint32_t*>(tstash + kStashMaskOfs) + (8 * 128 + row) * 8;
+                const uint4 m4 = *reinterpret_cast<const uint4*>(mrow);
+                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float* Wrgb = p.P + kernel_offset(LRGB);   // [128][3]
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float v[32];
+                    const uint32_t m = valid ? mm[g] : 0u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = 32 * g + i;
+                        float a = dzr[0] * __ldg(Wrgb + 3 * c) + dzr[1] * __ldg(Wrgb + 3 * c + 1) + dzr[2] * __ldg(Wrgb + 3 * c + 2);
+                        v[i] = (m >> i) & 1u ? a : 0.f;
+                    }
+                    uint8_t* chunk = act + (g >> 1) * kChunkBytes;
+                    const int u0 = (g & 1) * 4;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 o;
+                        o.x = pack2<kHalf>(v[8 * u + 0], v[8 * u + 1]);
+                        o.y = pack2<kHalf>(v[8 * u + 2], v[8 * u + 3]);
+                        o.z = pack2<kHalf>(v[8 * u + 4], v[8 * u + 5]);
+                        o.w = pack2<kHalf>(v[8 * u + 6], v[8 * u + 7]);
+                        *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = o;
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(act_ready);
+            pend_dst = gst + kGradChunkZ9 * kChunkBytes; pend_bytes = 2 * kChunkBytes;
+            pend_head = true; pend_head_dst = gst + kGradChunkHead * kChunkBytes;
+
+            for (int j = 0; j < kBwdJobs; ++j) {
+                // job boundary: ship what the previous step wrote, fetch this job's ReLU bitmask
+                named_bar_sync(1 + t, kTileRows);
+                issued = false;
+                if (row == 0) {
+                    if (pend_bytes) { bulk_s2g(pend_dst, act_saddr, pend_bytes); issued = true; }
+                    if (pend_head) { bulk_s2g(pend_head_dst, head_saddr, kChunkBytes); issued = true; }
+                    if (issued) bulk_commit_group();
+                }
+                pend_bytes = 0; pend_head = false;
+                // output of job j is dZ of: j=0 -> dense_8 (no mask), j>=1 -> dense_{8-j} masked by Y_{8-j} > 0
+                uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (j >= 1) {
+                    const uint4* mrow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(tstash + kStashMaskOfs) + ((8 - j) * 128 + row) * 8);
+                    const uint4 a = mrow[0], b = mrow[1];
+                    mask[0] = a.x; mask[1] = a.y; mask[2] = a.z; mask[3] = a.w;
+                    mask[4] = b.x; mask[5] = b.y; mask[6] = b.z; mask[7] = b.w;
+                }
+                if (row == 0 && issued) bulk_wait_read_all();
+                named_bar_sync(1 + t, kTileRows);
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                if (j == 0) bwd_epilogue_cols<kHalf, false, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
+                else if (j == 1) bwd_epilogue_cols<kHalf, true, true>(tmem_row, act, row, mask, s_wsig, dzs, valid);
+                else bwd_epilogue_cols<kHalf, true, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
+                tc_fence_before();
+                fence_proxy_async();
+                if (j + 1 < kBwdJobs) mbar_arrive(act_ready);     // dZ_0 (j = 8) feeds no further MMA
+                pend_dst = gst + (j == 0 ? kGradChunkZ8 : grad_chunk_Z(8 - j)) * kChunkBytes;
+                pend_bytes = 4 * kChunkBytes;
+            }
+        }
+        named_bar_sync(1 + t, kTileRows);
+        if (row == 0) {
+            if (pend_bytes) bulk_s2g(pend_dst, act_saddr, pend_bytes);
+            if (pend_head) bulk_s2g(pend_head_dst, head_saddr, kChunkBytes);
+            bulk_commit_group();
+            bulk_wait_all();
+        }
+    }
+    __syncthreads();
+    if (warp == kBMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// =============================================================================================
+// 2. weight-gradient kernel: dW = X^T . dZ with MN-major operands (K = rows)
+struct DwJob {
+    int x_chunk0, x_nchunks;      // X_l chunk images in the activation stash (1, 2 or 4 chunks of 64 features)
+    int dz_chunk0, dz_nchunks;    // dZ_l chunk images in the gradient stash (1, 2 or 4 chunks of 64 columns)
+    int layer;                    // Layer enum of the Keras kernel receiving the gradient
+    int k_row0, k_rows;           // rows [k_row0, k_row0 + k_rows) of that kernel come from X features [0, k_rows)
+    int n_col0, n_cols;           // kernel columns [0, n_cols) come from dZ columns [n_col0, n_col0 + n_cols)
+    int bias_layer;               // Layer enum receiving colsum(dZ) (same column mapping), or -1
+};
+constexpr int kDwJobs = 14;
+static void build_dw_jobs(DwJob* j) {
+    int n = 0;
+    j[n++] = DwJob{kStashChunkEncXyz, 1, grad_chunk_Z(0), 4, L0, 0, 63, 0, 256, L0};
+    for (int l = 1; l <= 7; ++l) j[n++] = DwJob{stash_chunk_Y(l - 1), 4, grad_chunk_Z(l), 4, l, 0, 256, 0, 256, l};
+    j[n++] = DwJob{kStashChunkEncXyz, 1, grad_chunk_Z(5), 4, L5, 256, 63, 0, 256, -1};
+    j[n++] = DwJob{stash_chunk_Y(7), 4, kGradChunkZ8, 4, L8, 0, 256, 0, 256, L8};
+    j[n++] = DwJob{stash_chunk_Y(7), 4, kGradChunkHead, 1, LSIGMA, 0, 256, 3, 1, LSIGMA};
+    j[n++] = DwJob{kStashChunkBott, 4, kGradChunkZ9, 2, L9, 0, 256, 0, 128, L9};
+    j[n++] = DwJob{kStashChunkEncDir, 1, kGradChunkZ9, 2, L9, 256, 27, 0, 128, -1};
+    j[n++] = DwJob{kStashChunkY9, 2, kGradChunkHead, 1, LRGB, 0, 128, 0, 3, LRGB};
+}
+
+constexpr int kDwStageRows = 64;                       // rows (= UMMA K) per pipeline stage: 4 K-steps of 16
+constexpr int kDwHalfChunk = kChunkBytes / 2;          // 64 rows of a chunk image = 8 KB
+constexpr int kDwStageBytes = 8 * kDwHalfChunk;        // up to 4 X half-chunks + 4 dZ half-chunks = 64 KB
+constexpr int kDwStages = 3;
+constexpr int kDwSmemBar = kDwStages * kDwStageBytes;  // 192 KB
+constexpr int kDwSmemBias = kDwSmemBar + 128;          // 256 fp32 column sums
+constexpr int kDwSmemTotal = kDwSmemBias + 1024;
+constexpr int kDwThreads = 192;                        // warps 0-3: bias + flush, warp 4: producer, warp 5: MMA
+
+struct DwParams {
+    DwJob job;
+    const uint8_t* stash; const uint8_t* gstash;
+    float* partial;          // [grid][512 x 256] fp32 accumulator dump (M-block major)
+    float* bias_partial;     // [grid][256]
+    int num_tiles;
+};
+
+// MN-major SWIZZLE_128B descriptor: 64-element (128 B) atoms along MN `lbo` bytes apart, 8-row groups along K 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int fmt, int N) {   // both operands MN-major, M = 128
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+template <bool kHalf>
+__global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbar = sbase + kDwSmemBar;   // full[3], empty[3], done
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kDwSmemBar + 8 * 8);
+    float* s_bias = reinterpret_cast<float*>(smem + kDwSmemBias);
+    const DwJob jb = p.job;
+    const int xn = jb.x_nchunks == 1 ? 2 : jb.x_nchunks;      // a single X chunk is loaded twice to fill M = 128
+    const int mblocks = xn / 2;
+    const int N = jb.dz_nchunks * 64;
+    const uint32_t stage_tx = (uint32_t)(xn + jb.dz_nchunks) * kDwHalfChunk;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kDwStages; ++s) { mbar_init(sbar + 8 * s, 1); mbar_init(sbar + 8 * (kDwStages + s), 1 + 4); }
+        mbar_init(sbar + 8 * 6, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int nstages = my_tiles * 2;           // two 64-row stages per tile
+    constexpr int fmt = kHalf ? 0 : 1;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < nstages; ++it) {
+                const int tile = blockIdx.x + (it >> 1) * gridDim.x;
+                const uint32_t half = (uint32_t)(it & 1) * kDwHalfChunk;
+                const uint8_t* xs = p.stash + (size_t)tile * kStashTileBytes + (size_t)jb.x_chunk0 * kChunkBytes + half;
+                const uint8_t* zs = p.gstash + (size_t)tile * kGradTileBytes + (size_t)jb.dz_chunk0 * kChunkBytes + half;
+                mbar_wait(sbar + 8 * (kDwStages + stage), phase ^ 1);
+                mbar_expect_tx(sbar + 8 * stage, stage_tx);
+                const uint32_t dst = sbase + stage * kDwStageBytes;
+                for (int c = 0; c < xn; ++c)
+                    bulk_g2s(dst + c * kDwHalfChunk, xs + (size_t)(jb.x_nchunks == 1 ? 0 : c) * kChunkBytes, kDwHalfChunk, sbar + 8 * stage);
+                for (int c = 0; c < jb.dz_nchunks; ++c)
+                    bulk_g2s(dst + (4 + c) * kDwHalfChunk, zs + (size_t)c * kChunkBytes, kDwHalfChunk, sbar + 8 * stage);
+                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_mn(fmt, N);
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < nstages; ++it) {
+                mbar_wait(sbar + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t xb = sbase + stage * kDwStageBytes, zb = xb + 4 * kDwHalfChunk;
+#pragma unroll 1
+                for (int mb = 0; mb < mblocks; ++mb) {
+#pragma unroll
+                    for (int k = 0; k < kDwStageRows / 16; ++k) {
+                        // K-step k covers rows [16k, 16k+16): two 8-row groups = 2048 B further into every atom
+                        const uint64_t ad = umma_desc_mn(xb + mb * 2 * kDwHalfChunk + k * 2048, kDwHalfChunk);
+                        const uint64_t bd = umma_desc_mn(zb + k * 2048, kDwHalfChunk);
+                        umma_f16(tmem_base + (uint32_t)(mb * 256), ad, bd, idesc, (it == 0 && k == 0) ? 0u : 1u);
+                    }
+                }
+                umma_commit(sbar + 8 * (kDwStages + stage));
+                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(sbar + 8 * 6);
+        }
+    } else {
+        // ---- warps 0-3: bias gradient = column sums of dZ over this CTA's rows, read from the same smem stages
+        const int tid = threadIdx.x;             // 0..127 -> columns tid and tid + 128
+        float s0 = 0.f, s1 = 0.f;
+        uint32_t stage = 0, phase = 0;
+        const bool want_bias = jb.bias_layer >= 0;
+        for (int it = 0; it < nstages; ++it) {
+            mbar_wait(sbar + 8 * stage, phase);
+            if (want_bias) {
+                const uint8_t* zb = smem + stage * kDwStageBytes + 4 * kDwHalfChunk;
+#pragma unroll 4
+                for (int r = 0; r < kDwStageRows; ++r) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = tid + 128 * h;
+                        if (col < N) {
+                            const uint8_t* cz = zb + (col >> 6) * kDwHalfChunk + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
+                            float v;
+                            if (kHalf) v = __half2float(*reinterpret_cast<const __half*>(cz));
+                            else v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cz));
+                            if (h == 0) s0 += v; else s1 += v;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) mbar_arrive(sbar + 8 * (kDwStages + stage));     // one arrive per warp (count 1 + 4)
+            __syncwarp();
+            if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+        }
+        if (want_bias) {
+            p.bias_partial[(size_t)blockIdx.x * 256 + tid] = s0;
+            p.bias_partial[(size_t)blockIdx.x * 256 + tid + 128] = s1;
+        }
+        // ---- flush the accumulators: thread = TMEM lane = X feature within the M-block
+        if (nstages > 0) {
+            mbar_wait(sbar + 8 * 6, 0);
+            tc_fence_after();
+        }
+        float* dst = p.partial + (size_t)blockIdx.x * 512 * 256;
+        for (int mb = 0; mb < mblocks; ++mb) {
+            float* drow = dst + ((size_t)mb * 128 + warp * 32 + lane) * 256;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t r[32];
+                if (nstages > 0) {
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * 256 + c0), r);
+                    tmem_ld_wait(r);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<uint4*>(drow + c0 + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// 3. reduce the per-CTA partials of one job into the flat gradient buffer (+=)
+__global__ void reduce_grads_kernel(DwJob jb, int grid, const float* __restrict__ partial, const float* __restrict__ bias_partial,
+                                    float* __restrict__ G /* one model */) {
+    const int fan_out = layer_dim(jb.layer).fan_out;
+    const int total = jb.k_rows * jb.n_cols;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const int m = i / jb.n_cols, n = i - m * jb.n_cols;
+        const size_t src = ((size_t)(m >> 7) * 128 + (m & 127)) * 256 + jb.n_col0 + n;
+        float s = 0.f;
+        for (int c = 0; c < grid; ++c) s += partial[(size_t)c * 512 * 256 + src];
+        G[kernel_offset(jb.layer) + (size_t)(jb.k_row0 + m) * fan_out + n] += s;
+    } else if (jb.bias_layer >= 0 && i < total + jb.n_cols) {
+        const int n = i - total;
+        float s = 0.f;
+        for (int c = 0; c < grid; ++c) s += bias_partial[(size_t)c * 256 + jb.n_col0 + n];
+        G[bias_offset(jb.bias_layer) + n] += s;
+    }
+}
+
+// =============================================================================================
+// host side
+static bool g_bwd_table_uploaded = false;
+
+int tc_train_create(nerfb200_ctx* ctx) {
+    const BwdTable& t = bwd_table();
+    for (int pz = 0; pz < 2; ++pz)
+        for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc(&ctx->packed_bwd[pz][m], (size_t)t.bytes * ctx->replicas));
+    if (!g_bwd_table_uploaded) {
+        NB_CUDA(cudaMemcpyToSymbol(c_bwd_chunks, t.c, sizeof(BwdChunk) * kBwdMaxChunks));
+        NB_CUDA(cudaMemcpyToSymbol(c_bwd_job_begin, t.job_begin, sizeof(int) * (kBwdJobs + 1)));
+        g_bwd_table_uploaded = true;
+    }
+    NB_CUDA(cudaFuncSetAttribute(bwd_data_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(bwd_data_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemTotal));
+    return 0;
+}
+
+void tc_train_destroy(nerfb200_ctx* ctx) {
+    for (int pz = 0; pz < 2; ++pz)
+        for (int m = 0; m < 2; ++m) if (ctx->packed_bwd[pz][m]) cudaFree(ctx->packed_bwd[pz][m]);
+}
+
+int tc_train_pack(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st) {
+    const BwdTable& t = bwd_table();
+    const int64_t units = (int64_t)t.n * (kChunkBytes / 16);
+    for (int m = 0; m < 2; ++m) {
+        const float* P = flat_params + (int64_t)m * kParamsPerModel;
+        pack_bwd_weights_kernel<__nv_bfloat16><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[0][m], t.n);
+        pack_bwd_weights_kernel<__half><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[1][m], t.n);
+        for (int pz = 0; pz < 2; ++pz)
+            for (int r = 1; r < ctx->replicas; ++r)
+                NB_CUDA(cudaMemcpyAsync((uint8_t*)ctx->packed_bwd[pz][m] + (size_t)r * t.bytes, ctx->packed_bwd[pz][m], t.bytes,
+                                        cudaMemcpyDeviceToDevice, st));
+    }
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+static inline int64_t tiles_of(int64_t R) { return (R + kTileRows - 1) / kTileRows; }
+
+int64_t tc_stash_bytes(int64_t R) { return tiles_of(R) * (int64_t)kStashTileBytes; }
+
+// backward workspace: gradient stash + per-CTA accumulator dumps for the 14 dW jobs
+static int64_t dw_partial_floats(int grid) { return (int64_t)grid * 512 * 256; }
+int64_t tc_workspace_bytes(int64_t R, int training) {
+    if (!training) return 0;
+    const int grid = num_sms();
+    return tiles_of(R) * (int64_t)kGradTileBytes + kDwJobs * (dw_partial_floats(grid) + (int64_t)grid * 256) * 4;
+}
+
+int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
+                const float* flat_params, const float* d_rgb, const float* d_sigma, float* flat_grads, void* workspace, void* stash,
+                cudaStream_t st) {
+    (void)ro; (void)rd; (void)t;
+    if (!ctx->packed_valid) { set_error("mlp_backward: pack_weights has not been called"); return NERFB200_ESTATE; }
+    NB_CHECK_ARG(workspace && stash, "mlp_backward: workspace and stash required");
+    const int64_t R = B * S;
+    if (R == 0) return 0;
+    const int num_tiles = (int)tiles_of(R);
+    const int sms = ctx->num_sms;
+    uint8_t* gstash = (uint8_t*)workspace;
+    float* partial0 = (float*)(gstash + (size_t)num_tiles * kGradTileBytes);
+    const float* P = flat_params + (int64_t)which * kParamsPerModel;
+    float* G = flat_grads + (int64_t)which * kParamsPerModel;
+
+    BwdParams bp;
+    bp.wimg = (const uint8_t*)ctx->packed_bwd[half ? 1 : 0][which];
+    bp.wimg_stride = bwd_table().bytes; bp.replicas = ctx->replicas;
+    bp.P = P; bp.stash = (const uint8_t*)stash; bp.gstash = gstash; bp.d_rgb = d_rgb; bp.d_sigma = d_sigma; bp.R = R; bp.num_tiles = num_tiles;
+    const int pairs = (num_tiles + 1) / 2;
+    const int grid = pairs < sms ? pairs : sms;
+    if (half) bwd_data_kernel<true><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
+    else bwd_data_kernel<false><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
+    NB_LAUNCH_CHECK();
+
+    DwJob jobs[kDwJobs];
+    build_dw_jobs(jobs);
+    const int dgrid = num_tiles < sms ? num_tiles : sms;
+    for (int j = 0; j < kDwJobs; ++j) {
+        DwParams dp;
+        dp.job = jobs[j]; dp.stash = (const uint8_t*)stash; dp.gstash = gstash; dp.num_tiles = num_tiles;
+        dp.partial = partial0 + (size_t)j * (dw_partial_floats(dgrid) + (size_t)dgrid * 256);
+        dp.bias_partial = dp.partial + dw_partial_floats(dgrid);
+        if (half) dw_kernel<true><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
+        else dw_kernel<false><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
+        NB_LAUNCH_CHECK();
+        const int total = jobs[j].k_rows * jobs[j].n_cols + jobs[j].n_cols;
+        reduce_grads_kernel<<<(total + 255) / 256, 256, 0, st>>>(jobs[j], dgrid, dp.partial, dp.bias_partial, G);
+        NB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace nb

@@ -168,3 +168,43 @@ def test_fit_evaluate_surface_and_loss_decreases():
     assert after > before + 1.0, (before, after)
     assert len(hist.history["psnr_metric"]) == 3 and "val_psnr_metric" in hist.history and "loss" in hist.history
     assert nerf.optimizer.iterations == 24
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_train_step_tensor_core_vs_oracle(golden, precision):
+    """Tensor-core training step (forward stash -> backward-data -> weight-gradient kernels -> fused Adam)
+    vs the fp32 autograd oracle. Stated tolerance (SURVEY.md App. E3 form): loss within 5e-3 relative,
+    global gradient cosine >= 0.999, every one of the 48 gradient tensors cosine >= 0.98."""
+    g = golden["oracle_forward_train"]
+    nerf = make_nerf(om.init_weights(7), precision, train_precision=precision)
+    ref = make_nerf(om.init_weights(7), "fp32")
+    dv = lambda k: dev(g[k])
+    args = (dv("rays_o"), dv("rays_d"), dv("near"), dv("far"), dv("rgb_gt"))
+    loss, _, _ = nerf._loss_and_grads(*args, u_fine=dv("u_fine"))
+    loss32, _, _ = ref._loss_and_grads(*args, u_fine=dv("u_fine"))
+    assert abs(float(loss.item()) - float(g["train_loss"])) <= 5e-3 * float(g["train_loss"])
+    a, b = nerf.flat_grads.double(), ref.flat_grads.double()
+    assert torch.isfinite(a).all()
+    assert float(torch.nn.functional.cosine_similarity(a, b, dim=0)) >= 0.999
+    for v in nerf.trainable_variables:
+        x, y = a[v._ofs:v._ofs + v._n], b[v._ofs:v._ofs + v._n]
+        assert float(torch.nn.functional.cosine_similarity(x, y, dim=0)) >= 0.98, v.name
+    # gradient norms also agree with the fp32 autograd oracle's
+    gn = np.array([float(torch.linalg.vector_norm(a[v._ofs:v._ofs + v._n])) for v in nerf.trainable_variables])
+    assert np.all(np.abs(gn - g["train_grad_norms"]) <= 0.15 * g["train_grad_norms"] + 1e-7)
+    # and the full step runs through the public surface
+    logs = nerf.train_step(((g["rays_o"], g["rays_d"], g["near"], g["far"]), (g["rgb_gt"],)), u_fine=dv("u_fine"))
+    assert nerf.optimizer.iterations == 1 and np.isfinite(logs["psnr_metric"])
+
+
+def test_tensor_core_training_reduces_loss():
+    H = W = 16
+    v = osc.synthetic_view(H, W, view=0)
+    gt = np.tile(np.array([[0.2, 0.5, 0.8]], F32), (H * W, 1))
+    nerf = nb.setup_model(nb.make_params({"system": {"white_bg": False}}), precision="bf16", train_precision="bf16", seed=1)
+    ds = nb.RayDataset.from_tensor_slices(((v["rays_o"], v["rays_d"], v["near"], v["far"]), (gt,))).shuffle(seed=0).repeat().batch(128, drop_remainder=True)
+    val = nb.RayDataset.from_tensor_slices(((v["rays_o"], v["rays_d"], v["near"], v["far"]), (gt,))).batch(128)
+    before = nerf.evaluate(val)
+    nerf.fit(x=ds, epochs=2, steps_per_epoch=16)
+    after = nerf.evaluate(val)
+    assert after > before + 1.0, (before, after)
