@@ -339,6 +339,43 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_
 }
 
 
+
+// Inference epilogue with packed arithmetic: add.f32x2 for the bias, one cvt per pair, ReLU as max on the
+// packed 16-bit pair (rounding is monotonic and sign preserving, so max(cvt(x), 0) == cvt(max(x, 0))).
+template <bool kHalf, int NG, bool kRelu>
+__device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const float* s_bias, uint8_t* act, int row) {
+    uint32_t r[2][32];
+    tmem_ld32(tmem_row, r[0]);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        uint32_t (&rr)[32] = r[g & 1];
+        tmem_ld_wait(rr);
+        if (g + 1 < NG) tmem_ld32(tmem_row + (uint32_t)(32 * (g + 1)), r[(g + 1) & 1]);
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + 32 * g);
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i];
+            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1])), make_float2(bb.x, bb.y));
+            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(bb.z, bb.w));
+            if (kHalf) {
+                __half2 h0 = __floats2half2_rn(s0.x, s0.y), h1 = __floats2half2_rn(s1.x, s1.y);
+                if (kRelu) { const __half2 z = __floats2half2_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
+                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            } else {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(s0.x, s0.y), h1 = __floats2bfloat162_rn(s1.x, s1.y);
+                if (kRelu) { const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
+                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+        }
+        uint8_t* chunk = act + (g >> 1) * 16384;
+        const int u0 = (g & 1) * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+    }
+}
+
 #define NB_T0() long long _t0 = dbg_on ? clock64() : 0
 #define NB_T1(slot) do { if (dbg_on) dbg_acc##slot += (unsigned long long)(clock64() - _t0); } while (0)
 
@@ -586,6 +623,213 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
     }
 }
 
+
+// =============================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): the two CTAs of a cluster (an SM pair) run ONE M=256 MMA per
+// instruction -- each CTA contributes its own 128-row tile as A and HALF of the layer's weights as B --
+// so per SM the weight stream, the operand reads from shared memory and the number of MMA instructions
+// all halve, and every instruction carries 128 cycles of tensor work (above the ~78-cycle issue floor).
+// Roles per CTA are as in the single-CTA kernel; only the leader's warp 9 issues MMAs, the peer's warp 9
+// relays "my half of the weight stage has landed" to the leader's ring barrier. tcgen05.commit multicasts
+// completion to both CTAs' barriers.
+template <bool kHalf>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_forward_pair_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool dbg_on = p.dbg != nullptr && blockIdx.x < 2;
+    unsigned long long dbg_acc0 = 0, dbg_acc1 = 0, dbg_acc2 = 0, dbg_acc3 = 0;
+    const long long t_kernel0 = clock64();
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbar = sbase + kSmemBar;
+    auto ring_full = [&](int s) { return sbar + 8 * s; };
+    auto ring_empty = [&](int s) { return sbar + 8 * (kStages + s); };
+    auto act_ready = [&](int t) { return sbar + 8 * (2 * kStages + t); };
+    auto acc_full = [&](int t) { return sbar + 8 * (2 * kStages + 2 + t); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemBar + 8 * (2 * kStages + 4));
+
+    if (threadIdx.x == 0) {
+        // leader's ring_full: own expect_tx arrive + the peer's relay; peer's ring_full: own arrive only
+        for (int s = 0; s < kStages; ++s) { mbar_init(ring_full(s), rank == 0 ? 2 : 1); mbar_init(ring_empty(s), 1); }
+        // act_ready (used in the leader): one elected arrive per CTA; acc_full: one multicast commit
+        for (int t = 0; t < 2; ++t) { mbar_init(act_ready(t), 2); mbar_init(acc_full(t), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int quads = (p.num_tiles + 3) >> 2;          // a cluster works on 4 tiles at a time: 2 slots x 2 CTAs
+    constexpr int fmt = kHalf ? 0 : 1;
+
+    if (warp == kProducerWarp) {
+        // ===================== weight producer: this CTA's half of every chunk =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int qd = cluster_id; qd < quads; qd += num_clusters) {
+                const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;   // slots with a tile in at least one CTA
+                for (int j = 0; j < kNumJobs; ++j) {
+                    const int cb = c_job_begin[j];
+                    const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
+                    // a layer whose weights fit the ring (KC <= 4) is loaded ONCE and used by both slots
+                    const int loads = (KC <= kStages) ? 1 : nslots;
+                    for (int rep = 0; rep < loads; ++rep)
+                        for (int kc = 0; kc < KC; ++kc) {
+                            // N = 256 layers: chunk (nh = rank, kc); dense_9 / rgb: my half of the rows of chunk kc
+                            uint32_t gofs, bytes;
+                            if (j < 9) { gofs = c_chunks[cb + (int)rank * KC + kc].gofs; bytes = 16384; }
+                            else if (j == 9) { gofs = c_chunks[cb + kc].gofs + rank * 8192u; bytes = 8192; }
+                            else { gofs = c_chunks[cb + kc].gofs + rank * 1024u; bytes = 1024; }
+                            mbar_wait(ring_empty(stage), phase ^ 1);
+                            mbar_expect_tx(ring_full(stage), bytes);
+                            bulk_g2s(sbase + kSmemRing + stage * kStageBytes, p.wimg + gofs, bytes, ring_full(stage));
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0 && rank == 1) {
+            // ===================== peer: relay "stage landed" to the leader =====================
+            uint32_t stage = 0, phase = 0;
+            for (int qd = cluster_id; qd < quads; qd += num_clusters) {
+                const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;
+                for (int j = 0; j < kNumJobs; ++j) {
+                    const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
+                    const int loads = ((KC <= kStages) ? 1 : nslots) * KC;
+                    for (int c = 0; c < loads; ++c) {
+                        mbar_wait(ring_full(stage), phase);
+                        mbar_arrive_cluster(mapa(ring_full(stage), 0));
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            // ===================== leader: MMA issuer for the pair =====================
+            const uint32_t ring_lo = ((sbase + kSmemRing) >> 4) & 0x3FFFu;
+            constexpr uint32_t id256 = umma_idesc_pair(fmt, 256), id128 = umma_idesc_pair(fmt, 128), id16 = umma_idesc_pair(fmt, 16);
+            uint32_t stage = 0, phase = 0, act_phase_bits = 0;
+            for (int qd = cluster_id; qd < quads; qd += num_clusters) {
+#pragma unroll 1
+                for (int j = 0; j < kNumJobs; ++j) {
+                    const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
+                    const int enc_kc = (j == 0) ? 0 : (j == 5 || j == 9) ? 4 : -1;
+                    const bool enc_short = (j == 9);
+                    const uint32_t idesc = (j < 9) ? id256 : (j == 9) ? id128 : id16;
+                    const bool shared_w = KC <= kStages;                     // weights loaded once for both slots
+                    const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;
+                    const uint32_t stage0 = stage, phase0 = phase;
+#pragma unroll 1
+                    for (int t = 0; t < nslots; ++t) {
+                        { NB_T0(); mbar_wait_cluster(act_ready(t), (act_phase_bits >> t) & 1u); NB_T1(0); }
+                        act_phase_bits ^= 1u << t;
+                        tc_fence_after();
+                        const uint32_t act_lo = ((sbase + kSmemAct + t * kActBytes) >> 4) & 0x3FFFu;
+                        const uint32_t enc_lo = ((sbase + kSmemEnc + t * kEncBytes) >> 4) & 0x3FFFu;
+                        const uint32_t d = tmem_base + (uint32_t)(t * 256);
+                        if (shared_w) { stage = stage0; phase = phase0; }     // second slot re-walks the same stages
+                        const bool first_user = !shared_w || t == 0, last_user = !shared_w || t == nslots - 1;
+#pragma unroll 1
+                        for (int kc = 0; kc < KC; ++kc) {
+                            if (first_user) { NB_T0(); mbar_wait_cluster(ring_full(stage), phase); NB_T1(1); tc_fence_after(); }
+                            const bool is_enc = kc == enc_kc;
+                            const uint32_t a_lo = is_enc ? enc_lo : act_lo + (uint32_t)(kc * 1024);
+                            const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+                            if (!(is_enc && enc_short)) {
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                            }
+                            if (last_user) umma_commit_pair(ring_empty(stage));
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit_pair(acc_full(t));
+                    }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // ===================== epilogue warps (identical in both CTAs) =====================
+        const int t = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        uint8_t* act = smem + kSmemAct + t * kActBytes;
+        uint8_t* enc = smem + kSmemEnc + t * kEncBytes;
+        float* s_bias = reinterpret_cast<float*>(smem + kSmemBias + t * 1024);
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+        const uint32_t act_ready_leader = mapa(act_ready(t), 0);
+        uint32_t acc_phase = 0;
+        const float4* ws4 = reinterpret_cast<const float4*>(p.heads + HeadOffsets::wsigma);
+        RowCtx cur, nxt;
+        // tile of (quad, slot, rank); a tile index past the end is a dummy: rows clamped, nothing stored
+        auto tile_of = [&](int qd) { return qd * 4 + t * 2 + (int)rank; };
+        int qd = cluster_id;
+        if (qd < quads && qd * 4 + t * 2 < p.num_tiles) prep_tile<kHalf>(p, tile_of(qd), row, enc, cur);
+        for (; qd < quads; qd += num_clusters) {
+            if (qd * 4 + t * 2 >= p.num_tiles) continue;
+            float sig_acc = 0.f;
+            for (int j = 0; j < kNumJobs; ++j) {
+                // job boundary: everything the previous step wrote (encoding / activations) is complete and fenced
+                named_bar_sync(1 + t, kTileRows);
+                if (row == 0) mbar_arrive_cluster(act_ready_leader);      // this CTA's operand for job j is ready
+                {
+                    const int N = j < 9 ? 256 : (j == 9 ? 128 : 16);
+                    const float* b = p.heads + HeadOffsets::bias(j);
+                    if (row < N) s_bias[row] = __ldg(b + row);
+                    if (row + 128 < N) s_bias[row + 128] = __ldg(b + row + 128);
+                }
+                named_bar_sync(1 + t, kTileRows);
+                { NB_T0(); mbar_wait(acc_full(t), acc_phase); NB_T1(0); }
+                acc_phase ^= 1;
+                tc_fence_after();
+                long long _te = dbg_on ? clock64() : 0;
+                if (j < 10) {
+                    if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc);
+                    else if (j == 8) epilogue_cols_packed<kHalf, 8, false>(tmem_row, s_bias, act, row);
+                    else if (j == 9) epilogue_cols_packed<kHalf, 4, true>(tmem_row, s_bias, act, row);
+                    else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row);
+                    if (j == 5) write_enc_dir<kHalf>(cur.dir, enc, row);
+                    if (j == 7 && cur.valid) p.sigma[cur.grow] = fmaxf(sig_acc + __ldg(p.heads + HeadOffsets::bsigma), 0.f);
+                    tc_fence_before();
+                    fence_proxy_async();
+                    if (dbg_on) dbg_acc1 += (unsigned long long)(clock64() - _te);
+                    if (j == 9) {
+                        const int nq = qd + num_clusters;
+                        if (nq < quads && nq * 4 + t * 2 < p.num_tiles) prep_tile<kHalf>(p, tile_of(nq), row, enc, nxt);
+                    }
+                } else {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_row, r);
+                    tmem_ld_wait(r);
+                    if (cur.valid) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float x = __uint_as_float(r[c]) + s_bias[c];
+                            p.rgb[3 * cur.grow + c] = 1.f / (1.f + expf(-x));
+                        }
+                    }
+                    tc_fence_before();
+                }
+            }
+            cur = nxt;
+        }
+    }
+    if (dbg_on && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == 0 || warp == 4)) {
+        int rowi = (warp == kProducerWarp ? 0 : warp == kMmaWarp ? 1 : warp == 0 ? 2 : 3);
+        unsigned long long* o = p.dbg + blockIdx.x * 32 + rowi * 8;
+        o[0] = dbg_acc0; o[1] = dbg_acc1; o[2] = dbg_acc2; o[3] = dbg_acc3; o[4] = (unsigned long long)(clock64() - t_kernel0);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
 // ---------------------------------------------------------------------------------------------
 static bool g_table_uploaded = false;
 static int upload_table() {
@@ -615,6 +859,8 @@ int tc_create(nerfb200_ctx* ctx) {
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     return tc_train_create(ctx);
 }
 
@@ -666,10 +912,16 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
     p.dbg = nullptr;
     p.dbg_mode = debug ? atoi(getenv("NERFB200_TC_DEBUG")) : 0;
     if (debug) {
-        NB_CUDA(cudaMalloc((void**)&p.dbg, 32 * sizeof(unsigned long long)));
-        NB_CUDA(cudaMemsetAsync(p.dbg, 0, 32 * sizeof(unsigned long long), st));
+        NB_CUDA(cudaMalloc((void**)&p.dbg, 64 * sizeof(unsigned long long)));
+        NB_CUDA(cudaMemsetAsync(p.dbg, 0, 64 * sizeof(unsigned long long), st));
     }
-    if (stash) {
+    static const bool use_pair = getenv("NERFB200_TC_PAIR") ? atoi(getenv("NERFB200_TC_PAIR")) != 0 : true;
+    if (use_pair && !stash) {
+        int quads = (p.num_tiles + 3) / 4;
+        int clusters = quads < ctx->num_sms / 2 ? quads : ctx->num_sms / 2;
+        if (half) mlp_tc_forward_pair_kernel<true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+        else mlp_tc_forward_pair_kernel<false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+    } else if (stash) {
         if (half) mlp_tc_forward_kernel<true, true><<<grid, kThreads, kSmemTotal, st>>>(p);
         else mlp_tc_forward_kernel<false, true><<<grid, kThreads, kSmemTotal, st>>>(p);
     } else {
@@ -678,15 +930,15 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
     }
     NB_LAUNCH_CHECK();
     if (debug) {
-        unsigned long long h[32];
+        unsigned long long h[64];
         NB_CUDA(cudaMemcpyAsync(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
         NB_CUDA(cudaStreamSynchronize(st));
         cudaFree(p.dbg);
         const char* names[4] = {"producer", "mma", "epi0", "epi1"};
         fprintf(stderr, "[tc debug] tiles=%d grid=%d (block 0 cycles)\n", p.num_tiles, grid);
-        for (int r = 0; r < 4; ++r)
-            fprintf(stderr, "  %-8s wait0=%llu wait1/epi=%llu biasbar=%llu prep=%llu total=%llu\n", names[r], h[r * 8], h[r * 8 + 1],
-                    h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
+        for (int r = 0; r < 8; ++r)
+            fprintf(stderr, "  cta%d %-8s wait0=%llu wait1/epi=%llu biasbar=%llu prep=%llu total=%llu\n", r / 4, names[r % 4], h[r * 8],
+                    h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
     }
     return 0;
 }
