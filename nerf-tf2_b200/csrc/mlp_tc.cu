@@ -536,12 +536,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
                     if (row < N) s_bias[row] = __ldg(b + row);
                     if (row + 128 < N) s_bias[row + 128] = __ldg(b + row + 128);
                 }
-                if (kTrain && issued) bulk_wait_read_all();   // the sources may be overwritten after the next barrier
                 named_bar_sync(1 + t, kTileRows);
                 if (dbg_on) dbg_acc2 += (unsigned long long)(clock64() - _tb);
                 { NB_T0(); mbar_wait(acc_full(t), acc_phase); NB_T1(0); }
                 acc_phase ^= 1;
                 tc_fence_after();
+                if (kTrain) {
+                    // the bulk stores issued at the job boundary had the whole MMA to drain; their sources are
+                    // overwritten by the epilogue below, so make sure they have been read
+                    if (issued) bulk_wait_read_all();
+                    named_bar_sync(1 + t, kTileRows);
+                }
                 long long _te = dbg_on ? clock64() : 0;
                 if (j < 10 && p.dbg_mode == 2) {
                     tc_fence_before();
@@ -632,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
 // Roles per CTA are as in the single-CTA kernel; only the leader's warp 9 issues MMAs, the peer's warp 9
 // relays "my half of the weight stage has landed" to the leader's ring barrier. tcgen05.commit multicasts
 // completion to both CTAs' barriers.
-template <bool kHalf>
+template <bool kHalf, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_forward_pair_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -767,17 +772,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
         uint32_t acc_phase = 0;
         const float4* ws4 = reinterpret_cast<const float4*>(p.heads + HeadOffsets::wsigma);
         RowCtx cur, nxt;
+        uint8_t* pendA_dst = nullptr; uint32_t pendA_bytes = 0;      // training: queued bulk stores (see the single-CTA kernel)
+        uint8_t* pendE_dst = nullptr; uint32_t pendE_bytes = 0;
+        const uint32_t act_saddr = sbase + kSmemAct + t * kActBytes, enc_saddr = sbase + kSmemEnc + t * kEncBytes;
         // tile of (quad, slot, rank); a tile index past the end is a dummy: rows clamped, nothing stored
         auto tile_of = [&](int qd) { return qd * 4 + t * 2 + (int)rank; };
         int qd = cluster_id;
-        if (qd < quads && qd * 4 + t * 2 < p.num_tiles) prep_tile<kHalf>(p, tile_of(qd), row, enc, cur);
+        if (qd < quads && qd * 4 + t * 2 < p.num_tiles) {
+            prep_tile<kHalf>(p, tile_of(qd), row, enc, cur);
+            if (kTrain && tile_of(qd) < p.num_tiles) { pendE_dst = p.stash + (size_t)tile_of(qd) * kStashTileBytes + kStashChunkEncXyz * 16384; pendE_bytes = 16384; }
+        }
         for (; qd < quads; qd += num_clusters) {
             if (qd * 4 + t * 2 >= p.num_tiles) continue;
+            const bool real_tile = tile_of(qd) < p.num_tiles;
+            uint8_t* tstash = (kTrain && real_tile) ? p.stash + (size_t)tile_of(qd) * kStashTileBytes : nullptr;
             float sig_acc = 0.f;
             for (int j = 0; j < kNumJobs; ++j) {
                 // job boundary: everything the previous step wrote (encoding / activations) is complete and fenced
                 named_bar_sync(1 + t, kTileRows);
                 if (row == 0) mbar_arrive_cluster(act_ready_leader);      // this CTA's operand for job j is ready
+                bool issued = false;
+                if (kTrain && row == 0) {
+                    if (pendA_bytes) { bulk_s2g(pendA_dst, act_saddr, pendA_bytes); issued = true; }
+                    if (pendE_bytes) { bulk_s2g(pendE_dst, enc_saddr, pendE_bytes); issued = true; }
+                    if (issued) bulk_commit_group();
+                }
+                pendA_bytes = 0; pendE_bytes = 0;
                 {
                     const int N = j < 9 ? 256 : (j == 9 ? 128 : 16);
                     const float* b = p.heads + HeadOffsets::bias(j);
@@ -788,36 +808,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                 { NB_T0(); mbar_wait(acc_full(t), acc_phase); NB_T1(0); }
                 acc_phase ^= 1;
                 tc_fence_after();
+                if (kTrain) {
+                    if (issued) bulk_wait_read_all();
+                    named_bar_sync(1 + t, kTileRows);
+                }
                 long long _te = dbg_on ? clock64() : 0;
                 if (j < 10) {
-                    if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc);
-                    else if (j == 8) epilogue_cols_packed<kHalf, 8, false>(tmem_row, s_bias, act, row);
-                    else if (j == 9) epilogue_cols_packed<kHalf, 4, true>(tmem_row, s_bias, act, row);
-                    else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row);
-                    if (j == 5) write_enc_dir<kHalf>(cur.dir, enc, row);
-                    if (j == 7 && cur.valid) p.sigma[cur.grow] = fmaxf(sig_acc + __ldg(p.heads + HeadOffsets::bsigma), 0.f);
+                    if (kTrain) {
+                        uint32_t* mrow = nullptr;
+                        if (tstash && j != 8) mrow = reinterpret_cast<uint32_t*>(tstash + kStashMaskOfs) + ((j == 9 ? 8 : j) * 128 + row) * 8;
+                        if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
+                        else if (j == 8) epilogue_cols<kHalf, 8, false, false>(tmem_row, s_bias, act, row, ws4, sig_acc);
+                        else if (j == 9) epilogue_cols<kHalf, 4, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
+                        else epilogue_cols<kHalf, 8, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
+                        if (tstash) {
+                            pendA_dst = tstash + (j < 8 ? stash_chunk_Y(j) : j == 8 ? kStashChunkBott : kStashChunkY9) * 16384;
+                            pendA_bytes = j == 9 ? 2 * 16384 : 4 * 16384;
+                        }
+                    } else {
+                        if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc);
+                        else if (j == 8) epilogue_cols_packed<kHalf, 8, false>(tmem_row, s_bias, act, row);
+                        else if (j == 9) epilogue_cols_packed<kHalf, 4, true>(tmem_row, s_bias, act, row);
+                        else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row);
+                    }
+                    if (j == 5) {
+                        write_enc_dir<kHalf>(cur.dir, enc, row);
+                        if (kTrain && tstash) { pendE_dst = tstash + kStashChunkEncDir * 16384; pendE_bytes = 16384; }
+                    }
+                    if (j == 7) {
+                        const float sg = fmaxf(sig_acc + __ldg(p.heads + HeadOffsets::bsigma), 0.f);
+                        if (cur.valid) p.sigma[cur.grow] = sg;
+                        if (kTrain && tstash) reinterpret_cast<float*>(tstash + kStashOutOfs)[3 * 128 + row] = cur.valid ? sg : 0.f;
+                    }
                     tc_fence_before();
                     fence_proxy_async();
                     if (dbg_on) dbg_acc1 += (unsigned long long)(clock64() - _te);
                     if (j == 9) {
                         const int nq = qd + num_clusters;
-                        if (nq < quads && nq * 4 + t * 2 < p.num_tiles) prep_tile<kHalf>(p, tile_of(nq), row, enc, nxt);
+                        if (nq < quads && nq * 4 + t * 2 < p.num_tiles) {
+                            prep_tile<kHalf>(p, tile_of(nq), row, enc, nxt);
+                            if (kTrain && tile_of(nq) < p.num_tiles) { pendE_dst = p.stash + (size_t)tile_of(nq) * kStashTileBytes + kStashChunkEncXyz * 16384; pendE_bytes = 16384; }
+                        }
                     }
                 } else {
                     uint32_t r[32];
                     tmem_ld32(tmem_row, r);
                     tmem_ld_wait(r);
-                    if (cur.valid) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            float x = __uint_as_float(r[c]) + s_bias[c];
-                            p.rgb[3 * cur.grow + c] = 1.f / (1.f + expf(-x));
-                        }
+                    for (int c = 0; c < 3; ++c) {
+                        const float x = __uint_as_float(r[c]) + s_bias[c];
+                        const float y = 1.f / (1.f + expf(-x));
+                        if (cur.valid) p.rgb[3 * cur.grow + c] = y;
+                        if (kTrain && tstash) reinterpret_cast<float*>(tstash + kStashOutOfs)[3 * row + c] = cur.valid ? y : 0.f;
                     }
                     tc_fence_before();
                 }
             }
             cur = nxt;
+        }
+        if (kTrain) {
+            named_bar_sync(1 + t, kTileRows);
+            if (row == 0) {
+                if (pendA_bytes) bulk_s2g(pendA_dst, act_saddr, pendA_bytes);
+                if (pendE_bytes) bulk_s2g(pendE_dst, enc_saddr, pendE_bytes);
+                bulk_commit_group();
+                bulk_wait_all();
+            }
         }
     }
     if (dbg_on && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == 0 || warp == 4)) {
@@ -859,8 +915,10 @@ int tc_create(nerfb200_ctx* ctx) {
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     return tc_train_create(ctx);
 }
 
@@ -916,11 +974,16 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
         NB_CUDA(cudaMemsetAsync(p.dbg, 0, 64 * sizeof(unsigned long long), st));
     }
     static const bool use_pair = getenv("NERFB200_TC_PAIR") ? atoi(getenv("NERFB200_TC_PAIR")) != 0 : true;
-    if (use_pair && !stash) {
+    if (use_pair) {
         int quads = (p.num_tiles + 3) / 4;
         int clusters = quads < ctx->num_sms / 2 ? quads : ctx->num_sms / 2;
-        if (half) mlp_tc_forward_pair_kernel<true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
-        else mlp_tc_forward_pair_kernel<false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+        if (stash) {
+            if (half) mlp_tc_forward_pair_kernel<true, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+            else mlp_tc_forward_pair_kernel<false, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+        } else {
+            if (half) mlp_tc_forward_pair_kernel<true, false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+            else mlp_tc_forward_pair_kernel<false, false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+        }
     } else if (stash) {
         if (half) mlp_tc_forward_kernel<true, true><<<grid, kThreads, kSmemTotal, st>>>(p);
         else mlp_tc_forward_kernel<false, true><<<grid, kThreads, kSmemTotal, st>>>(p);

@@ -327,11 +327,12 @@ __global__ void __launch_bounds__(kBThreads, 1) bwd_data_kernel(const BwdParams 
                     mask[0] = a.x; mask[1] = a.y; mask[2] = a.z; mask[3] = a.w;
                     mask[4] = b.x; mask[5] = b.y; mask[6] = b.z; mask[7] = b.w;
                 }
-                if (row == 0 && issued) bulk_wait_read_all();
                 named_bar_sync(1 + t, kTileRows);
                 mbar_wait(acc_full, acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
+                if (row == 0 && issued) bulk_wait_read_all();     // the stores had the whole MMA to drain
+                named_bar_sync(1 + t, kTileRows);
                 if (j == 0) bwd_epilogue_cols<kHalf, false, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
                 else if (j == 1) bwd_epilogue_cols<kHalf, true, true>(tmem_row, act, row, mask, s_wsig, dzs, valid);
                 else bwd_epilogue_cols<kHalf, true, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
@@ -389,7 +390,7 @@ constexpr int kDwThreads = 192;                        // warps 0-3: bias + flus
 struct DwParams {
     DwJob job;
     const uint8_t* stash; const uint8_t* gstash;
-    float* partial;          // [grid][512 x 256] fp32 accumulator dump (M-block major)
+    float* partial;          // [grid][mblocks*128][N] fp32 accumulator dump (only the region this job produces)
     float* bias_partial;     // [grid][256]
     int num_tiles;
 };
@@ -512,9 +513,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
             mbar_wait(sbar + 8 * 6, 0);
             tc_fence_after();
         }
-        float* dst = p.partial + (size_t)blockIdx.x * 512 * 256;
+        float* dst = p.partial + (size_t)blockIdx.x * (size_t)(mblocks * 128) * N;
         for (int mb = 0; mb < mblocks; ++mb) {
-            float* drow = dst + ((size_t)mb * 128 + warp * 32 + lane) * 256;
+            float* drow = dst + ((size_t)mb * 128 + warp * 32 + lane) * N;
             for (int c0 = 0; c0 < N; c0 += 32) {
                 uint32_t r[32];
                 if (nstages > 0) {
@@ -541,11 +542,14 @@ __global__ void reduce_grads_kernel(DwJob jb, int grid, const float* __restrict_
     const int fan_out = layer_dim(jb.layer).fan_out;
     const int total = jb.k_rows * jb.n_cols;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xn = jb.x_nchunks == 1 ? 2 : jb.x_nchunks;
+    const int N = jb.dz_nchunks * 64;
+    const size_t per_cta = (size_t)(xn / 2) * 128 * N;
     if (i < total) {
         const int m = i / jb.n_cols, n = i - m * jb.n_cols;
-        const size_t src = ((size_t)(m >> 7) * 128 + (m & 127)) * 256 + jb.n_col0 + n;
+        const size_t src = (size_t)m * N + jb.n_col0 + n;
         float s = 0.f;
-        for (int c = 0; c < grid; ++c) s += partial[(size_t)c * 512 * 256 + src];
+        for (int c = 0; c < grid; ++c) s += partial[(size_t)c * per_cta + src];
         G[kernel_offset(jb.layer) + (size_t)(jb.k_row0 + m) * fan_out + n] += s;
     } else if (jb.bias_layer >= 0 && i < total + jb.n_cols) {
         const int n = i - total;
