@@ -171,6 +171,21 @@ NERFB200_API int nerfb200_adam_step(int64_t n, float* params, const float* grads
 NERFB200_API int nerfb200_depth_type2(int H, int W, const double* K, const double* c2w, double scale_factor,
                          const float* pred_depth, float* out, void* stream);
 
+/* ---- callers either side of the path -----------------------------------
+ * next-2, sample-mode training input (core/base_dataset.py:555-621): B uniform pixel ids in
+ * [0, n_pixels) (tf.random.uniform(..., dtype=int32) -> Philox(seed, step)); rays of those pixels come
+ * from nerfb200_get_rays_at; colours are gathered from a device-resident uint8 [H*W,3] image as
+ * float(img)/255 (:596-598). */
+NERFB200_API int nerfb200_sample_pixels(int64_t B, int64_t n_pixels, uint64_t seed, uint64_t step,
+                                        int32_t* pixel_ids, void* stream);
+NERFB200_API int nerfb200_gather_rgb_u8(int64_t B, const uint8_t* image, const int32_t* pixel_ids,
+                                        float* rgb, void* stream);
+/* next-3, per-view post-processing (main/eval.py:53-64, main/render.py:96-100): out_u8 =
+ * uint8(clip(pred*255,0,255)) and, if gt_u8 is given, *sq_err += sum((gt/255 - clip(pred*255,0,255)/255)^2)
+ * over the n_values = H*W*3 channel values (psnr_metric_numpy = -10*log10(sq_err / n_values)). */
+NERFB200_API int nerfb200_postprocess_rgb(int64_t n_values, const float* pred_rgb, const uint8_t* gt_u8,
+                                          uint8_t* out_u8, double* sq_err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,9 @@ SIGNATURES = {
     "nerfb200_mse_loss_grad": (_i32, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_adam_step": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "nerfb200_depth_type2": (_i32, [_i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _dbl, _vp, _vp, _vp]),
+    "nerfb200_sample_pixels": (_i32, [_i64, _i64, _u64, _u64, _vp, _vp]),
+    "nerfb200_gather_rgb_u8": (_i32, [_i64, _vp, _vp, _vp, _vp]),
+    "nerfb200_postprocess_rgb": (_i32, [_i64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -11,13 +11,23 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
 
 
-def _stale():
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+def _source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive a snapshot copy)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [
         os.path.join(HERE, "..", "include", "nerfb200.h"), os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale():
+    if not os.path.exists(OUT) or not os.path.exists(OUT + ".hash"):
+        return True
+    return open(OUT + ".hash").read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -42,6 +52,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libnerfb200.so")
     cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
     subprocess.check_call(cmd)
+    with open(OUT + ".hash", "w") as f:
+        f.write(_source_hash())
     return OUT
 
 

@@ -181,6 +181,46 @@ __global__ void depth_type2_kernel(int W, int64_t n, CamD cam, CamD inv, double 
     out[i] = (float)(inv.c2w[8] * p0 + inv.c2w[9] * p1 + inv.c2w[10] * p2 + inv.c2w[11]);
 }
 
+
+// ---- callers either side of the path ---------------------------------------
+// next-2: sample-mode training input (core/base_dataset.py:555-621): B uniform pixel ids in [0, n_pixels)
+// (Philox, like tf.random.uniform(..., dtype=int32)), and the gather of their colours from a uint8 image.
+__global__ void sample_pixels_kernel(int64_t B, uint32_t n_pixels, uint64_t seed, uint64_t step, int32_t* __restrict__ ids) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    uint4 r = philox4x32_10(make_uint4((uint32_t)(i >> 2), (uint32_t)((uint64_t)(i >> 2) >> 32), (uint32_t)step, 2u),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    uint32_t x = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+    ids[i] = (int32_t)(((uint64_t)x * (uint64_t)n_pixels) >> 32);        // unbiased enough for n_pixels << 2^32
+}
+__global__ void gather_rgb_u8_kernel(int64_t B, const uint8_t* __restrict__ img, const int32_t* __restrict__ ids,
+                                     float* __restrict__ rgb) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 3) return;
+    int64_t r = i / 3;
+    int c = (int)(i - r * 3);
+    rgb[i] = __fdiv_rn((float)img[(int64_t)ids[r] * 3 + c], 255.0f);      // cast then / 255.0 (:596-598)
+}
+// next-3: per-view post-processing of main/eval.py:53-64 and main/render.py:96-100 on the device:
+// img_u8 = uint8(clip(pred*255, 0, 255)); sq_err += sum((gt/255 - clip(pred*255,0,255)/255)^2) for PSNR.
+__global__ void postprocess_rgb_kernel(int64_t n, const float* __restrict__ pred, const uint8_t* __restrict__ gt,
+                                       uint8_t* __restrict__ out, double* __restrict__ sq_err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float e = 0.f;
+    if (i < n) {
+        float v = fminf(fmaxf(__fmul_rn(pred[i], 255.0f), 0.0f), 255.0f);
+        if (out) out[i] = (uint8_t)v;                                     // astype(np.uint8) truncates
+        if (gt) {
+            float d = __fsub_rn(__fdiv_rn((float)gt[i], 255.0f), __fdiv_rn(v, 255.0f));
+            e = d * d;
+        }
+    }
+    if (sq_err && gt) {
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0 && e != 0.f) atomicAdd(sq_err, (double)e);
+    }
+}
+
 static inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace nb
@@ -268,6 +308,35 @@ int nerfb200_positional_encode(int64_t R, int L, const float* x, float* out, voi
     if (R == 0) return 0;
     NB_CHECK_ARG(x && out, "positional_encode: NULL pointer");
     posenc_kernel<<<blocks_for(R * (3 + 6 * L), 256), 256, 0, (cudaStream_t)stream>>>(R, L, x, out);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+
+int nerfb200_sample_pixels(int64_t B, int64_t n_pixels, uint64_t seed, uint64_t step, int32_t* pixel_ids, void* stream) {
+    NB_CHECK_ARG(B >= 0 && n_pixels > 0 && n_pixels < ((int64_t)1 << 31), "sample_pixels: bad shape");
+    if (B == 0) return 0;
+    NB_CHECK_ARG(pixel_ids != nullptr, "sample_pixels: NULL output");
+    sample_pixels_kernel<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, (uint32_t)n_pixels, seed, step, pixel_ids);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nerfb200_gather_rgb_u8(int64_t B, const uint8_t* image, const int32_t* pixel_ids, float* rgb, void* stream) {
+    NB_CHECK_ARG(B >= 0, "gather_rgb_u8: bad shape");
+    if (B == 0) return 0;
+    NB_CHECK_ARG(image && pixel_ids && rgb, "gather_rgb_u8: NULL pointer");
+    gather_rgb_u8_kernel<<<blocks_for(B * 3, 256), 256, 0, (cudaStream_t)stream>>>(B, image, pixel_ids, rgb);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int nerfb200_postprocess_rgb(int64_t n_values, const float* pred_rgb, const uint8_t* gt_u8, uint8_t* out_u8, double* sq_err,
+                             void* stream) {
+    NB_CHECK_ARG(n_values >= 0, "postprocess_rgb: bad shape");
+    if (n_values == 0) return 0;
+    NB_CHECK_ARG(pred_rgb != nullptr && (out_u8 || (gt_u8 && sq_err)), "postprocess_rgb: nothing to do");
+    postprocess_rgb_kernel<<<blocks_for(n_values, 256), 256, 0, (cudaStream_t)stream>>>(n_values, pred_rgb, gt_u8, out_u8, sq_err);
     NB_LAUNCH_CHECK();
     return 0;
 }

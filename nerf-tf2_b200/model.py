@@ -240,6 +240,14 @@ class NeRF:
             var.assign(w[var.name])
         self._dirty = True
 
+    def set_everything(self, load_dir=None, load_tag=None, skip_optimizer=False):
+        """NeRF.set_everything (core/model.py:239-287); paths default to params.model.load.*"""
+        from . import checkpoint
+        load = getattr(getattr(self.params, "model", None), "load", None)
+        load_dir = load_dir if load_dir is not None else load.load_dir
+        load_tag = load_tag if load_tag is not None else load.load_tag
+        checkpoint.set_everything(self, load_dir, load_tag, skip_optimizer)
+
     def _sync_packed(self):
         if self._dirty:
             check(load().nerfb200_pack_weights(self._ctx, ptr(self.flat_params), stream_ptr()), "pack_weights")

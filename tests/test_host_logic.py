@@ -60,3 +60,21 @@ def test_psnr_functions():
     assert abs(float(nb.psnr_metric(torch.from_numpy(y), torch.from_numpy(p))) - rm.psnr_metric_numpy(y, p)) < 1e-4
     m.reset_states()
     assert m.state.sum() == 0
+
+
+def test_checkpoint_file_format(tmp_path):
+    """CustomSaver._save_weights format (core/ops.py:110-120): name -> array plus an ordered `names` array."""
+    from nerf_tf2_b200 import checkpoint
+
+    class V:
+        def __init__(self, name, a):
+            self.name, self._a = name, a
+
+        def numpy(self):
+            return self._a
+    vs = [V("coarse/dense_0/kernel", np.ones((63, 256), np.float32)), V("coarse/dense_0/bias", np.zeros(256, np.float32))]
+    path = tmp_path / "w.npz"
+    checkpoint.save_weights(str(path), vs)
+    d = np.load(path)
+    assert [str(n) for n in d["names"]] == ["coarse/dense_0/kernel", "coarse/dense_0/bias"]
+    assert d["coarse/dense_0/kernel"].shape == (63, 256)
