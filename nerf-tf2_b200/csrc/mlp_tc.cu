@@ -886,6 +886,328 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
     if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
+
+// =============================================================================================
+// v3: chunk-pipelined 2-CTA kernel (inference). One 128-row tile per CTA (256 rows per cluster), TWO
+// accumulator buffers in TMEM that alternate by layer, EIGHT epilogue warps (two per TMEM lane quadrant,
+// each pair splitting the columns) and one "activation chunk ready" barrier per 64 columns: the MMAs of
+// layer l+1 on K chunk c are issued as soon as the epilogue of layer l has produced columns [64c, 64c+64),
+// so the tensor core works on layer l+1 while layer l is still being drained -- the overlap comes from
+// the layer's own K loop instead of from a second tile, which frees shared memory for an 8-deep weight ring.
+constexpr int k3Stages = 8;
+constexpr int k3SmemAct = 0;                                   // 64 KB
+constexpr int k3SmemEnc = k3SmemAct + kActBytes;               // 16 KB
+constexpr int k3SmemRing = k3SmemEnc + kEncBytes;              // 8 x 16 KB
+constexpr int k3SmemBar = k3SmemRing + k3Stages * kStageBytes;
+constexpr int k3SmemBias = k3SmemBar + 256;                    // all biases + sigma head of the model (fp32)
+constexpr int k3SmemSig = k3SmemBias + ((HeadOffsets::total * 4 + 15) / 16) * 16;
+constexpr int k3SmemTotal = k3SmemSig + 128 * 4;
+static_assert(k3SmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+
+// encoding of one half (32 features) of the 64-column enc_xyz row: half 0 = [x,y,z, pairs 0..13, sin 14],
+// half 1 = [cos 14, pairs 15..29, 0]; pair p = (d = p / 10, l = p % 10) -> sin, cos of x_d * 2^l * pi
+template <bool kHalf>
+__device__ __forceinline__ void write_enc_xyz_half(const float (&xyz)[3], int half, uint8_t* enc, int row) {
+    float e[32];
+    if (half == 0) {
+        e[0] = xyz[0]; e[1] = xyz[1]; e[2] = xyz[2];
+#pragma unroll
+        for (int pp = 0; pp < 15; ++pp) {
+            const int d = pp / 10, l = pp % 10;
+            float sn, cs;
+            sincosf(__fmul_rn(xyz[d], __fmul_rn((float)(1 << l), 3.14159274101257324f)), &sn, &cs);
+            e[3 + 2 * pp] = sn;
+            if (pp < 14) e[4 + 2 * pp] = cs;
+        }
+    } else {
+#pragma unroll
+        for (int pp = 14; pp < 30; ++pp) {
+            const int d = pp / 10, l = pp % 10;
+            float sn, cs;
+            sincosf(__fmul_rn(xyz[d], __fmul_rn((float)(1 << l), 3.14159274101257324f)), &sn, &cs);
+            if (pp > 14) e[2 * pp - 29] = sn;
+            e[2 * pp - 28] = cs;
+        }
+        e[31] = 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        uint4 v;
+        v.x = pack2<kHalf>(e[8 * u + 0], e[8 * u + 1]);
+        v.y = pack2<kHalf>(e[8 * u + 2], e[8 * u + 3]);
+        v.z = pack2<kHalf>(e[8 * u + 4], e[8 * u + 5]);
+        v.w = pack2<kHalf>(e[8 * u + 6], e[8 * u + 7]);
+        *reinterpret_cast<uint4*>(enc + swz(row, half * 4 + u)) = v;
+    }
+}
+
+// one 64-column activation chunk (two groups of 32 accumulator columns) of this thread's row
+template <bool kHalf, bool kRelu, bool kSigma>
+__device__ __forceinline__ void v3_drain_chunk(uint32_t tmem_cols, const float* bias, uint8_t* chunk, int row, const float* wsig,
+                                               float& sig_acc) {
+    uint32_t r[2][32];
+    tmem_ld32(tmem_cols, r[0]);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint32_t (&rr)[32] = r[g];
+        tmem_ld_wait(rr);
+        if (g == 0) tmem_ld32(tmem_cols + 32u, r[1]);
+        const float4* b4 = reinterpret_cast<const float4*>(bias + 32 * g);
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 bb = b4[i];
+            float2 s0 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1])), make_float2(bb.x, bb.y));
+            float2 s1 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(bb.z, bb.w));
+            if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
+                const float4 w = reinterpret_cast<const float4*>(wsig + 32 * g)[i];
+                sig_acc = fmaf(fmaxf(s0.x, 0.f), w.x, sig_acc);
+                sig_acc = fmaf(fmaxf(s0.y, 0.f), w.y, sig_acc);
+                sig_acc = fmaf(fmaxf(s1.x, 0.f), w.z, sig_acc);
+                sig_acc = fmaf(fmaxf(s1.y, 0.f), w.w, sig_acc);
+            }
+            if (kHalf) {
+                __half2 h0 = __floats2half2_rn(s0.x, s0.y), h1 = __floats2half2_rn(s1.x, s1.y);
+                if (kRelu) { const __half2 z = __floats2half2_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
+                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            } else {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(s0.x, s0.y), h1 = __floats2bfloat162_rn(s1.x, s1.y);
+                if (kRelu) { const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
+                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(chunk + swz(row, g * 4 + u)) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+    }
+}
+
+template <bool kHalf>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_forward_v3_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbar = sbase + k3SmemBar;
+    const bool dbg_on = p.dbg != nullptr && blockIdx.x < 2;
+    unsigned long long dbg_acc0 = 0, dbg_acc1 = 0, dbg_acc2 = 0, dbg_acc3 = 0;
+    const long long t_kernel0 = clock64();
+    auto ring_full = [&](int s) { return sbar + 8 * s; };
+    auto ring_empty = [&](int s) { return sbar + 8 * (k3Stages + s); };
+    auto chunk_ready = [&](int c) { return sbar + 8 * (2 * k3Stages + c); };      // leader: 4 warps x 2 CTAs
+    const uint32_t enc_ready = sbar + 8 * (2 * k3Stages + 4);                     // leader: 8 warps x 2 CTAs
+    auto acc_full = [&](int b) { return sbar + 8 * (2 * k3Stages + 5 + b); };     // both CTAs (multicast commit)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + k3SmemBar + 8 * (2 * k3Stages + 7));
+    float* s_heads = reinterpret_cast<float*>(smem + k3SmemBias);
+    float* s_sig = reinterpret_cast<float*>(smem + k3SmemSig);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < k3Stages; ++s) { mbar_init(ring_full(s), rank == 0 ? 2 : 1); mbar_init(ring_empty(s), 1); }
+        for (int c = 0; c < 4; ++c) mbar_init(chunk_ready(c), 8);
+        mbar_init(enc_ready, 16);
+        mbar_init(acc_full(0), 1); mbar_init(acc_full(1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < HeadOffsets::total; i += kThreads) s_heads[i] = __ldg(p.heads + i);
+    cluster_sync_all();
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int num_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int tpairs = (p.num_tiles + 1) >> 1;          // a cluster works on 2 tiles at a time (one per CTA)
+    constexpr int fmt = kHalf ? 0 : 1;
+
+    // chunk list of job j in ISSUE order: the chunk fed from the encoding buffer goes first (it is ready long
+    // before the activations), then the activation chunks 0..3. kc_of(j, i) = K-chunk index in the packed image.
+    auto n_chunks = [](int j) { return (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4; };
+    auto kc_of = [](int j, int i) { return (j == 5 || j == 9) ? (i == 0 ? 4 : i - 1) : i; };
+
+    if (warp == kProducerWarp) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tp = cluster_id; tp < tpairs; tp += num_clusters)
+                for (int j = 0; j < kNumJobs; ++j) {
+                    const int cb = c_job_begin[j], NC = n_chunks(j);
+                    for (int i = 0; i < NC; ++i) {
+                        const int kc = kc_of(j, i);
+                        uint32_t gofs, bytes;
+                        if (j < 9) { gofs = c_chunks[cb + (int)rank * NC + kc].gofs; bytes = 16384; }
+                        else if (j == 9) { gofs = c_chunks[cb + kc].gofs + rank * 8192u; bytes = 8192; }
+                        else { gofs = c_chunks[cb + kc].gofs + rank * 1024u; bytes = 1024; }
+                        mbar_wait(ring_empty(stage), phase ^ 1);
+                        mbar_expect_tx(ring_full(stage), bytes);
+                        bulk_g2s(sbase + k3SmemRing + stage * kStageBytes, p.wimg + gofs, bytes, ring_full(stage));
+                        if (++stage == k3Stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0 && rank == 1) {
+            uint32_t stage = 0, phase = 0;
+            for (int tp = cluster_id; tp < tpairs; tp += num_clusters)
+                for (int j = 0; j < kNumJobs; ++j)
+                    for (int i = 0; i < n_chunks(j); ++i) {
+                        mbar_wait(ring_full(stage), phase);
+                        mbar_arrive_cluster(mapa(ring_full(stage), 0));
+                        if (++stage == k3Stages) { stage = 0; phase ^= 1; }
+                    }
+        } else if (lane == 0) {
+            const uint32_t ring_lo = ((sbase + k3SmemRing) >> 4) & 0x3FFFu;
+            const uint32_t act_lo = ((sbase + k3SmemAct) >> 4) & 0x3FFFu, enc_lo = ((sbase + k3SmemEnc) >> 4) & 0x3FFFu;
+            constexpr uint32_t id256 = umma_idesc_pair(fmt, 256), id128 = umma_idesc_pair(fmt, 128), id16 = umma_idesc_pair(fmt, 16);
+            uint32_t stage = 0, phase = 0, chunk_phase_bits = 0, enc_phase = 0;
+            for (int tp = cluster_id; tp < tpairs; tp += num_clusters) {
+#pragma unroll 1
+                for (int j = 0; j < kNumJobs; ++j) {
+                    const int NC = n_chunks(j);
+                    const bool has_enc = (j == 0 || j == 5 || j == 9);
+                    const uint32_t idesc = (j < 9) ? id256 : (j == 9) ? id128 : id16;
+                    const uint32_t d = tmem_base + (uint32_t)(((j == 10) ? 1 : (j & 1)) * 256);
+                    if (j == 0 || j == 9) { NB_T0(); mbar_wait_cluster(enc_ready, enc_phase); NB_T1(2); enc_phase ^= 1; tc_fence_after(); }
+#pragma unroll 1
+                    for (int i = 0; i < NC; ++i) {
+                        const bool is_enc = has_enc && i == 0;
+                        uint32_t a_lo;
+                        if (is_enc) a_lo = enc_lo;
+                        else {
+                            const int ac = has_enc && j != 0 ? i - 1 : i;            // activation chunk index
+                            { NB_T0(); mbar_wait_cluster(chunk_ready(ac), (chunk_phase_bits >> ac) & 1u); NB_T1(0); }
+                            chunk_phase_bits ^= 1u << ac;
+                            a_lo = act_lo + (uint32_t)(ac * 1024);
+                        }
+                        { NB_T0(); mbar_wait_cluster(ring_full(stage), phase); NB_T1(1); }
+                        tc_fence_after();
+                        const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
+                        umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, i == 0 ? 0u : 1u);
+                        umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+                        if (!(is_enc && j == 9)) {      // enc_dir is 32 columns: 2 K-steps
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                        }
+                        umma_commit_pair(ring_empty(stage));
+                        if (++stage == k3Stages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair(acc_full((j == 10) ? 1 : (j & 1)));
+                }
+            }
+        }
+    } else {
+        // ===================== 8 epilogue warps: group = warp >> 2 splits the columns, warp & 3 = TMEM lane quadrant
+        const int grp = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        uint8_t* act = smem + k3SmemAct;
+        uint8_t* enc = smem + k3SmemEnc;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t enc_ready_leader = mapa(enc_ready, 0);
+        uint32_t acc_phase_bits = 0;
+        const float* wsig = s_heads + HeadOffsets::wsigma;
+
+        auto load_row = [&](int tile, RowCtx& rc, float (&xyz)[3]) {
+            rc.grow = (int64_t)tile * kTileRows + row;
+            rc.valid = tile < p.num_tiles && rc.grow < p.R;
+            const int64_t lrow = rc.valid ? rc.grow : p.R - 1;
+            const int64_t ray = lrow / p.S;
+            const float tv = __ldg(p.t + lrow);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                rc.dir[d] = __ldg(p.rd + 3 * ray + d);
+                xyz[d] = __fadd_rn(__ldg(p.ro + 3 * ray + d), __fmul_rn(tv, rc.dir[d]));
+            }
+        };
+        auto signal = [&](uint32_t cluster_bar) {      // this warp's share of an operand is written: publish it
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(cluster_bar);
+        };
+
+        RowCtx cur, nxt;
+        int tp = cluster_id;
+        if (tp < tpairs) {
+            float xyz[3];
+            load_row(tp * 2 + (int)rank, cur, xyz);
+            write_enc_xyz_half<kHalf>(xyz, grp, enc, row);
+            signal(enc_ready_leader);
+        }
+        for (; tp < tpairs; tp += num_clusters) {
+            float sig_acc = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < kNumJobs; ++j) {
+                const int buf = (j == 10) ? 1 : (j & 1);
+                { NB_T0(); mbar_wait(acc_full(buf), (acc_phase_bits >> buf) & 1u); NB_T1(0); }
+                acc_phase_bits ^= 1u << buf;
+                tc_fence_after();
+                long long _te = dbg_on ? clock64() : 0;
+                const uint32_t tcols = tmem_lane + (uint32_t)(buf * 256);
+                const float* bias = s_heads + HeadOffsets::bias(j);
+                if (j < 9) {
+                    // N = 256: this group drains columns [128 grp, 128 grp + 128) = activation chunks 2 grp, 2 grp + 1
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int ch = grp * 2 + c;
+                        if (j == 7) v3_drain_chunk<kHalf, true, true>(tcols + 64u * ch, bias + 64 * ch, act + ch * 16384, row, wsig + 64 * ch, sig_acc);
+                        else if (j == 8) v3_drain_chunk<kHalf, false, false>(tcols + 64u * ch, bias + 64 * ch, act + ch * 16384, row, wsig, sig_acc);
+                        else v3_drain_chunk<kHalf, true, false>(tcols + 64u * ch, bias + 64 * ch, act + ch * 16384, row, wsig, sig_acc);
+                        signal(mapa(chunk_ready(ch), 0));
+                    }
+                    if (j == 5) {
+                        // dense_5 has consumed enc_xyz: the encoding buffer now takes enc_dir (32 features) + zeros
+                        if (grp == 0) {
+                            write_enc_dir<kHalf>(cur.dir, enc, row);          // writes all 8 units (4..7 = 0)
+                        }
+                        signal(enc_ready_leader);
+                    }
+                    if (j == 7) {
+                        if (grp == 1) s_sig[row] = sig_acc;
+                        named_bar_sync(1, 256);
+                        if (grp == 0 && cur.valid) p.sigma[cur.grow] = fmaxf(sig_acc + s_sig[row] + s_heads[HeadOffsets::bsigma], 0.f);
+                    }
+                } else if (j == 9) {
+                    // N = 128: group g drains columns [64 g, 64 g + 64) = activation chunk g
+                    v3_drain_chunk<kHalf, true, false>(tcols + 64u * grp, bias + 64 * grp, act + grp * 16384, row, wsig, sig_acc);
+                    signal(mapa(chunk_ready(grp), 0));
+                    // dense_9 has consumed enc_dir: encode the next tile now
+                    const int ntp = tp + num_clusters;
+                    if (ntp < tpairs) {
+                        float xyz[3];
+                        load_row(ntp * 2 + (int)rank, nxt, xyz);
+                        write_enc_xyz_half<kHalf>(xyz, grp, enc, row);
+                        signal(enc_ready_leader);
+                    }
+                } else {
+                    if (grp == 0) {
+                        uint32_t r[32];
+                        tmem_ld32(tcols, r);
+                        tmem_ld_wait(r);
+                        if (cur.valid) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float x = __uint_as_float(r[c]) + bias[c];
+                                p.rgb[3 * cur.grow + c] = 1.f / (1.f + expf(-x));
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                }
+                if (dbg_on) dbg_acc1 += (unsigned long long)(clock64() - _te);
+            }
+            cur = nxt;
+        }
+    }
+    if (dbg_on && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == 0 || warp == 4)) {
+        int rowi = (warp == kProducerWarp ? 0 : warp == kMmaWarp ? 1 : warp == 0 ? 2 : 3);
+        unsigned long long* o = p.dbg + blockIdx.x * 32 + rowi * 8;
+        o[0] = dbg_acc0; o[1] = dbg_acc1; o[2] = dbg_acc2; o[3] = dbg_acc3; o[4] = (unsigned long long)(clock64() - t_kernel0);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
 // ---------------------------------------------------------------------------------------------
 static bool g_table_uploaded = false;
 static int upload_table() {
@@ -919,6 +1241,8 @@ int tc_create(nerfb200_ctx* ctx) {
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemTotal));
     return tc_train_create(ctx);
 }
 
@@ -974,7 +1298,13 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
         NB_CUDA(cudaMemsetAsync(p.dbg, 0, 64 * sizeof(unsigned long long), st));
     }
     static const bool use_pair = getenv("NERFB200_TC_PAIR") ? atoi(getenv("NERFB200_TC_PAIR")) != 0 : true;
-    if (use_pair) {
+    static const bool use_v3 = getenv("NERFB200_TC_V3") ? atoi(getenv("NERFB200_TC_V3")) != 0 : false;
+    if (use_v3 && !stash) {
+        int tpairs = (p.num_tiles + 1) / 2;
+        int clusters = tpairs < ctx->num_sms / 2 ? tpairs : ctx->num_sms / 2;
+        if (half) mlp_tc_forward_v3_kernel<true><<<2 * clusters, kThreads, k3SmemTotal, st>>>(p);
+        else mlp_tc_forward_v3_kernel<false><<<2 * clusters, kThreads, k3SmemTotal, st>>>(p);
+    } else if (use_pair) {
         int quads = (p.num_tiles + 3) / 4;
         int clusters = quads < ctx->num_sms / 2 ? quads : ctx->num_sms / 2;
         if (stash) {

@@ -20,6 +20,8 @@
 #include "tc_common.cuh"
 #include "tc_layout.cuh"
 
+#include <stdlib.h>
+
 namespace nb {
 
 // =============================================================================================
@@ -355,6 +357,223 @@ __global__ void __launch_bounds__(kBThreads, 1) bwd_data_kernel(const BwdParams 
     if (warp == kBMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA variant of the backward-data kernel (tcgen05 cta_group::2, see mlp_tc_forward_pair_kernel): M = 256
+// MMAs across the CTA pair, each CTA streams HALF of W^T, and every weight stage is used by both slots.
+template <bool kHalf>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBThreads, 1) bwd_data_pair_kernel(const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sbar = sbase + kBSmemBar;
+    auto ring_full = [&](int s) { return sbar + 8 * s; };
+    auto ring_empty = [&](int s) { return sbar + 8 * (kBStages + s); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kBSmemBar + 8 * (2 * kBStages + 4));
+    float* s_wsig = reinterpret_cast<float*>(smem + kBSmemWsig);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBStages; ++s) { mbar_init(ring_full(s), rank == 0 ? 2 : 1); mbar_init(ring_empty(s), 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(sbar + 8 * (2 * kBStages + t), 2); mbar_init(sbar + 8 * (2 * kBStages + 2 + t), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 256) s_wsig[threadIdx.x] = p.P[kernel_offset(LSIGMA) + threadIdx.x];
+    cluster_sync_all();
+    if (warp == kBMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int num_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    const int quads = (p.num_tiles + 3) >> 2;
+    constexpr int fmt = kHalf ? 0 : 1;
+
+    if (warp == kBProducerWarp) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int qd = cluster_id; qd < quads; qd += num_clusters)
+                for (int j = 0; j < kBwdJobs; ++j) {
+                    const int KC = j == 0 ? 2 : 4;
+                    for (int kc = 0; kc < KC; ++kc) {          // loaded once, used by both slots
+                        mbar_wait(ring_empty(stage), phase ^ 1);
+                        mbar_expect_tx(ring_full(stage), kChunkBytes);
+                        bulk_g2s(sbase + kBSmemRing + stage * kChunkBytes,
+                                 p.wimg + c_bwd_chunks[c_bwd_job_begin[j] + (int)rank * KC + kc].gofs, kChunkBytes, ring_full(stage));
+                        if (++stage == kBStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == kBMmaWarp) {
+        if (lane == 0 && rank == 1) {
+            uint32_t stage = 0, phase = 0;
+            for (int qd = cluster_id; qd < quads; qd += num_clusters)
+                for (int j = 0; j < kBwdJobs; ++j) {
+                    const int KC = j == 0 ? 2 : 4;
+                    for (int kc = 0; kc < KC; ++kc) {
+                        mbar_wait(ring_full(stage), phase);
+                        mbar_arrive_cluster(mapa(ring_full(stage), 0));
+                        if (++stage == kBStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+        } else if (lane == 0) {
+            const uint32_t ring_lo = ((sbase + kBSmemRing) >> 4) & 0x3FFFu;
+            constexpr uint32_t idesc = umma_idesc_pair(fmt, 256);
+            uint32_t stage = 0, phase = 0, act_phase_bits = 0;
+            for (int qd = cluster_id; qd < quads; qd += num_clusters) {
+                const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;
+#pragma unroll 1
+                for (int j = 0; j < kBwdJobs; ++j) {
+                    const int KC = j == 0 ? 2 : 4;
+                    const uint32_t stage0 = stage, phase0 = phase;
+#pragma unroll 1
+                    for (int t = 0; t < nslots; ++t) {
+                        mbar_wait_cluster(sbar + 8 * (2 * kBStages + t), (act_phase_bits >> t) & 1u);
+                        act_phase_bits ^= 1u << t;
+                        tc_fence_after();
+                        const uint32_t act_lo = ((sbase + kBSmemAct + t * 4 * kChunkBytes) >> 4) & 0x3FFFu;
+                        const uint32_t d = tmem_base + (uint32_t)(t * 256);
+                        stage = stage0; phase = phase0;
+                        const bool first_user = t == 0, last_user = t == nslots - 1;
+#pragma unroll 1
+                        for (int kc = 0; kc < KC; ++kc) {
+                            if (first_user) { mbar_wait_cluster(ring_full(stage), phase); tc_fence_after(); }
+                            const uint32_t a_lo = act_lo + (uint32_t)(kc * 1024);
+                            const uint32_t b_lo = ring_lo + stage * (kChunkBytes >> 4);
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                            if (last_user) umma_commit_pair(ring_empty(stage));
+                            if (++stage == kBStages) { stage = 0; phase ^= 1; }
+                        }
+                        umma_commit_pair(sbar + 8 * (2 * kBStages + 2 + t));
+                    }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        const int t = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        uint8_t* act = smem + kBSmemAct + t * 4 * kChunkBytes;
+        uint8_t* head = smem + kBSmemHead + t * kChunkBytes;
+        const uint32_t act_saddr = sbase + kBSmemAct + t * 4 * kChunkBytes, head_saddr = sbase + kBSmemHead + t * kChunkBytes;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
+        const uint32_t act_ready_leader = mapa(sbar + 8 * (2 * kBStages + t), 0), acc_full = sbar + 8 * (2 * kBStages + 2 + t);
+        uint32_t acc_phase = 0;
+        uint8_t* pend_dst = nullptr; uint32_t pend_bytes = 0; bool pend_head = false; uint8_t* pend_head_dst = nullptr;
+
+        for (int qd = cluster_id; qd < quads; qd += num_clusters) {
+            if (qd * 4 + t * 2 >= p.num_tiles) continue;
+            const int tile = qd * 4 + t * 2 + (int)rank;
+            const bool real_tile = tile < p.num_tiles;                 // a dummy tile contributes zeros and stores nothing
+            const uint8_t* tstash = p.stash + (size_t)(real_tile ? tile : 0) * kStashTileBytes;
+            uint8_t* gst = p.gstash + (size_t)(real_tile ? tile : 0) * kGradTileBytes;
+            const int64_t grow = (int64_t)tile * kTileRows + row;
+            const bool valid = real_tile && grow < p.R;
+            const float* outs = reinterpret_cast<const float*>(tstash + kStashOutOfs);
+            float dzr[3] = {0.f, 0.f, 0.f}, dzs = 0.f;
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float y = outs[3 * row + c];
+                    dzr[c] = __ldg(p.d_rgb + 3 * grow + c) * y * (1.f - y);
+                }
+                dzs = outs[3 * 128 + row] > 0.f ? __ldg(p.d_sigma + grow) : 0.f;
+            }
+            // previous tile's last stores must have read smem before it is overwritten
+            named_bar_sync(1 + t, kTileRows);
+            if (row == 0) {
+                bool issued = false;
+                if (pend_bytes) { bulk_s2g(pend_dst, act_saddr, pend_bytes); issued = true; }
+                if (pend_head) { bulk_s2g(pend_head_dst, head_saddr, kChunkBytes); issued = true; }
+                if (issued) { bulk_commit_group(); bulk_wait_read_all(); }
+            }
+            pend_bytes = 0; pend_head = false;
+            named_bar_sync(1 + t, kTileRows);
+            {
+                uint4 o = make_uint4(pack2<kHalf>(dzr[0], dzr[1]), pack2<kHalf>(dzr[2], dzs), 0u, 0u);
+                *reinterpret_cast<uint4*>(head + swz(row, 0)) = o;
+#pragma unroll
+                for (int u = 1; u < 8; ++u) *reinterpret_cast<uint4*>(head + swz(row, u)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            {
+                const uint32_t* mrow = reinterpret_cast<const uint32_t*>(tstash + kStashMaskOfs) + (8 * 128 + row) * 8;
+                const uint4 m4 = *reinterpret_cast<const uint4*>(mrow);
+                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float* Wrgb = p.P + kernel_offset(LRGB);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float v[32];
+                    const uint32_t m = valid ? mm[g] : 0u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int c = 32 * g + i;
+                        float a = dzr[0] * __ldg(Wrgb + 3 * c) + dzr[1] * __ldg(Wrgb + 3 * c + 1) + dzr[2] * __ldg(Wrgb + 3 * c + 2);
+                        v[i] = (m >> i) & 1u ? a : 0.f;
+                    }
+                    uint8_t* chunk = act + (g >> 1) * kChunkBytes;
+                    const int u0 = (g & 1) * 4;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4 o;
+                        o.x = pack2<kHalf>(v[8 * u + 0], v[8 * u + 1]);
+                        o.y = pack2<kHalf>(v[8 * u + 2], v[8 * u + 3]);
+                        o.z = pack2<kHalf>(v[8 * u + 4], v[8 * u + 5]);
+                        o.w = pack2<kHalf>(v[8 * u + 6], v[8 * u + 7]);
+                        *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = o;
+                    }
+                }
+            }
+            fence_proxy_async();
+            if (real_tile) {
+                pend_dst = gst + kGradChunkZ9 * kChunkBytes; pend_bytes = 2 * kChunkBytes;
+                pend_head = true; pend_head_dst = gst + kGradChunkHead * kChunkBytes;
+            }
+            for (int j = 0; j < kBwdJobs; ++j) {
+                named_bar_sync(1 + t, kTileRows);                 // this CTA's operand for job j is complete and fenced
+                bool issued = false;
+                if (row == 0) {
+                    mbar_arrive_cluster(act_ready_leader);
+                    if (pend_bytes) { bulk_s2g(pend_dst, act_saddr, pend_bytes); issued = true; }
+                    if (pend_head) { bulk_s2g(pend_head_dst, head_saddr, kChunkBytes); issued = true; }
+                    if (issued) bulk_commit_group();
+                }
+                pend_bytes = 0; pend_head = false;
+                uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (j >= 1) {
+                    const uint4* mrow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(tstash + kStashMaskOfs) + ((8 - j) * 128 + row) * 8);
+                    const uint4 a = mrow[0], b = mrow[1];
+                    mask[0] = a.x; mask[1] = a.y; mask[2] = a.z; mask[3] = a.w;
+                    mask[4] = b.x; mask[5] = b.y; mask[6] = b.z; mask[7] = b.w;
+                }
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                if (row == 0 && issued) bulk_wait_read_all();
+                named_bar_sync(1 + t, kTileRows);
+                if (j == 0) bwd_epilogue_cols<kHalf, false, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
+                else if (j == 1) bwd_epilogue_cols<kHalf, true, true>(tmem_row, act, row, mask, s_wsig, dzs, valid);
+                else bwd_epilogue_cols<kHalf, true, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
+                tc_fence_before();
+                fence_proxy_async();
+                if (real_tile) { pend_dst = gst + (j == 0 ? kGradChunkZ8 : grad_chunk_Z(8 - j)) * kChunkBytes; pend_bytes = 4 * kChunkBytes; }
+            }
+        }
+        named_bar_sync(1 + t, kTileRows);
+        if (row == 0) {
+            if (pend_bytes) bulk_s2g(pend_dst, act_saddr, pend_bytes);
+            if (pend_head) bulk_s2g(pend_head_dst, head_saddr, kChunkBytes);
+            bulk_commit_group();
+            bulk_wait_all();
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == kBMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
 // =============================================================================================
 // 2. weight-gradient kernel: dW = X^T . dZ with MN-major operands (K = rows)
 struct DwJob {
@@ -574,6 +793,8 @@ int tc_train_create(nerfb200_ctx* ctx) {
     }
     NB_CUDA(cudaFuncSetAttribute(bwd_data_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(bwd_data_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(bwd_data_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(bwd_data_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(dw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemTotal));
     return 0;
@@ -633,7 +854,13 @@ int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const 
     bp.P = P; bp.stash = (const uint8_t*)stash; bp.gstash = gstash; bp.d_rgb = d_rgb; bp.d_sigma = d_sigma; bp.R = R; bp.num_tiles = num_tiles;
     const int pairs = (num_tiles + 1) / 2;
     const int grid = pairs < sms ? pairs : sms;
-    if (half) bwd_data_kernel<true><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
+    static const bool use_pair = getenv("NERFB200_TC_PAIR") ? atoi(getenv("NERFB200_TC_PAIR")) != 0 : true;
+    if (use_pair) {
+        const int quads = (num_tiles + 3) / 4;
+        const int clusters = quads < sms / 2 ? quads : sms / 2;
+        if (half) bwd_data_pair_kernel<true><<<2 * clusters, kBThreads, kBSmemTotal, st>>>(bp);
+        else bwd_data_pair_kernel<false><<<2 * clusters, kBThreads, kBSmemTotal, st>>>(bp);
+    } else if (half) bwd_data_kernel<true><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
     else bwd_data_kernel<false><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
     NB_LAUNCH_CHECK();
 
