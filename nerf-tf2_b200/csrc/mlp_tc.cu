@@ -716,8 +716,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     }
                 }
             }
-        } else if (lane == 0) {
+        } else if (rank == 0) {
             // ===================== leader: MMA issuer for the pair =====================
+            // the whole warp walks the loop (converged, so descriptors live in uniform registers and the
+            // compiler needs no per-instruction election loop); one elected lane issues the tcgen05 ops
             const uint32_t ring_lo = ((sbase + kSmemRing) >> 4) & 0x3FFFu;
             constexpr uint32_t id256 = umma_idesc_pair(fmt, 256), id128 = umma_idesc_pair(fmt, 128), id16 = umma_idesc_pair(fmt, 16);
             uint32_t stage = 0, phase = 0, act_phase_bits = 0;
@@ -747,16 +749,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                             const bool is_enc = kc == enc_kc;
                             const uint32_t a_lo = is_enc ? enc_lo : act_lo + (uint32_t)(kc * 1024);
                             const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
-                            if (!(is_enc && enc_short)) {
-                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
-                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                            if (elect_one_sync()) {
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+                                if (!(is_enc && enc_short)) {
+                                    umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+                                    umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                                }
+                                if (last_user) umma_commit_pair(ring_empty(stage));
+                                if (kc == KC - 1) umma_commit_pair(acc_full(t));
                             }
-                            if (last_user) umma_commit_pair(ring_empty(stage));
+                            __syncwarp();
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
-                        umma_commit_pair(acc_full(t));
                     }
                 }
             }

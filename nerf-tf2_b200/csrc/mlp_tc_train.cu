@@ -418,7 +418,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBThreads, 1) bwd_da
                         if (++stage == kBStages) { stage = 0; phase ^= 1; }
                     }
                 }
-        } else if (lane == 0) {
+        } else if (rank == 0) {
+            // converged warp, one elected lane issues (see mlp_tc_forward_pair_kernel)
             const uint32_t ring_lo = ((sbase + kBSmemRing) >> 4) & 0x3FFFu;
             constexpr uint32_t idesc = umma_idesc_pair(fmt, 256);
             uint32_t stage = 0, phase = 0, act_phase_bits = 0;
@@ -442,14 +443,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBThreads, 1) bwd_da
                             if (first_user) { mbar_wait_cluster(ring_full(stage), phase); tc_fence_after(); }
                             const uint32_t a_lo = act_lo + (uint32_t)(kc * 1024);
                             const uint32_t b_lo = ring_lo + stage * (kChunkBytes >> 4);
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
-                            if (last_user) umma_commit_pair(ring_empty(stage));
+                            if (elect_one_sync()) {
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
+                                if (last_user) umma_commit_pair(ring_empty(stage));
+                                if (kc == KC - 1) umma_commit_pair(sbar + 8 * (2 * kBStages + 2 + t));
+                            }
+                            __syncwarp();
                             if (++stage == kBStages) { stage = 0; phase ^= 1; }
                         }
-                        umma_commit_pair(sbar + 8 * (2 * kBStages + 2 + t));
                     }
                 }
             }
@@ -672,27 +676,30 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
+        {   // converged warp, one elected lane issues the tcgen05 ops
             const uint32_t idesc = umma_idesc_mn(fmt, N);
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < nstages; ++it) {
                 mbar_wait(sbar + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t xb = sbase + stage * kDwStageBytes, zb = xb + 4 * kDwHalfChunk;
+                if (elect_one_sync()) {
 #pragma unroll 1
-                for (int mb = 0; mb < mblocks; ++mb) {
+                    for (int mb = 0; mb < mblocks; ++mb) {
 #pragma unroll
-                    for (int k = 0; k < kDwStageRows / 16; ++k) {
-                        // K-step k covers rows [16k, 16k+16): two 8-row groups = 2048 B further into every atom
-                        const uint64_t ad = umma_desc_mn(xb + mb * 2 * kDwHalfChunk + k * 2048, kDwHalfChunk);
-                        const uint64_t bd = umma_desc_mn(zb + k * 2048, kDwHalfChunk);
-                        umma_f16(tmem_base + (uint32_t)(mb * 256), ad, bd, idesc, (it == 0 && k == 0) ? 0u : 1u);
+                        for (int k = 0; k < kDwStageRows / 16; ++k) {
+                            // K-step k covers rows [16k, 16k+16): two 8-row groups = 2048 B further into every atom
+                            const uint64_t ad = umma_desc_mn(xb + mb * 2 * kDwHalfChunk + k * 2048, kDwHalfChunk);
+                            const uint64_t bd = umma_desc_mn(zb + k * 2048, kDwHalfChunk);
+                            umma_f16(tmem_base + (uint32_t)(mb * 256), ad, bd, idesc, (it == 0 && k == 0) ? 0u : 1u);
+                        }
                     }
+                    umma_commit(sbar + 8 * (kDwStages + stage));
+                    if (it == nstages - 1) umma_commit(sbar + 8 * 6);
                 }
-                umma_commit(sbar + 8 * (kDwStages + stage));
+                __syncwarp();
                 if (++stage == kDwStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(sbar + 8 * 6);
         }
     } else {
         // ---- warps 0-3: bias gradient = column sums of dZ over this CTA's rows, read from the same smem stages

@@ -119,6 +119,18 @@ __device__ __forceinline__ uint32_t swz(int row, int unit) { return (uint32_t)(r
 constexpr int kTileRows = 128;
 constexpr int kChunkBytes = 16384;      // [128 rows x 64 K] 16-bit, 128 B per row, 16-byte units XOR-swizzled by (row & 7)
 
+// one lane of a converged warp (CUTLASS elect_one_sync)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t}"
+        : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
+
 // ---- thread-block-cluster helpers (CTA pairs, tcgen05 cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
