@@ -141,12 +141,12 @@ class KernelTimer:
             e0.record()
             out = fn(*a, **k)
             e1.record()
-            self.ev.setdefault(name, []).append((e0, e1, a, k))
+            self.ev.setdefault(name, []).append((e0, e1))
             return out
         return inner
 
     def totals(self):
-        return {n: (sum(e0.elapsed_time(e1) for e0, e1, _, _ in evs), len(evs)) for n, evs in self.ev.items()}
+        return {n: (sum(e0.elapsed_time(e1) for e0, e1 in evs), len(evs)) for n, evs in self.ev.items()}
 
 
 def run_b200(args):
@@ -185,13 +185,7 @@ def run_b200(args):
         nerf.render_rays(ro, rd, near, far, need_weights=False)
     barrier()
 
-    # ---- timed region 1: device-resident inputs, kernel path only (+ per-kernel CUDA events)
-    kt = KernelTimer(torch)
-    orig = (nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse)
-    nerf._mlp = kt.wrap("mlp", nerf._mlp)
-    ru.post_process_model_output = kt.wrap("composite", ru.post_process_model_output)
-    ru.sample_fine = kt.wrap("sample_fine", ru.sample_fine)
-    ru.sample_coarse = kt.wrap("sample_coarse", ru.sample_coarse)
+    # ---- timed region 1: device-resident inputs, the kernel path only -> `value`
     clocks = ClockSampler(local) if rank == 0 else None
     barrier()
     launches0 = lib.nerfb200_launch_count()
@@ -208,8 +202,25 @@ def run_b200(args):
     if world > 1:
         ms = nb.dist.max_over_ranks(ms, dev)
     clk = clocks.stop(tw0, tw1) if clocks else None
-    nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse = orig
     value = world * n_rays * args.steps / (ms / 1e3)
+
+    # ---- timed region 1b: the same K steps again with CUDA-event brackets around every C-ABI launch
+    # (on the launching stream) -> per-kernel durations for the roofline objects
+    kt = KernelTimer(torch)
+    orig = (nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse)
+    nerf._mlp = kt.wrap("mlp", nerf._mlp)
+    ru.post_process_model_output = kt.wrap("composite", ru.post_process_model_output)
+    ru.sample_fine = kt.wrap("sample_fine", ru.sample_fine)
+    ru.sample_coarse = kt.wrap("sample_coarse", ru.sample_coarse)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        nerf.render_rays(ro, rd, near, far, need_weights=False)
+    f1.record()
+    barrier()
+    ms_b = f0.elapsed_time(f1)
+    nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse = orig
 
     tot = kt.totals()
     mlp_ms, mlp_n = tot["mlp"]
@@ -221,18 +232,23 @@ def run_b200(args):
     sf_ms, sf_n = tot["sample_fine"]
     # weights 4Nc + bin edges 4(Nc+1) + t_coarse 4Nc read, t_sorted 4(Nc+Nf) written; u generated in-kernel
     sf_bytes = args.steps * n_rays * (4 * N_COARSE * 2 + 4 * (N_COARSE + 1) + 4 * (N_COARSE + N_FINE))
-    roofline = {"bound": "tensor", "kernel": "mlp_tc_forward_kernel (fused encoding + 8x256 MLP, coarse and fine launches)",
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_note = tj.get("mlp_dram_bytes_per_launch"), tj.get("note")
+    roofline = {"bound": "tensor", "kernel": "mlp_tc_forward_pair_kernel (fused encoding + 8x256 MLP on tcgen05 cta_group::2; coarse and fine launches)",
                 "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
                 "peak_kind": f"bf16 sustained, {pk['source']}", "frac_of_burst": mlp_tflops / pk["tensor_burst"],
-                "traffic": None, "launches": mlp_n, "avg_launch_ms": mlp_ms / mlp_n,
-                "share_of_step": mlp_ms / ms}
+                "traffic": traffic, "launches": mlp_n, "avg_launch_ms": mlp_ms / mlp_n,
+                "share_of_step": mlp_ms / ms_b, "traffic_note": traffic_note}
     roofline_hbm = [
         {"kernel": "composite_fwd_kernel", "bound": "hbm", "achieved": comp_bytes / (comp_ms / 1e3) / 1e9, "peak": pk["hbm"],
          "unit": "GB/s", "frac": comp_bytes / (comp_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": comp_n,
-         "share_of_step": comp_ms / ms},
+         "share_of_step": comp_ms / ms_b},
         {"kernel": "sample_fine_kernel", "bound": "hbm", "achieved": sf_bytes / (sf_ms / 1e3) / 1e9, "peak": pk["hbm"],
          "unit": "GB/s", "frac": sf_bytes / (sf_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": sf_n,
-         "share_of_step": sf_ms / ms},
+         "share_of_step": sf_ms / ms_b},
     ]
 
     # ---- timed region 2: end to end through NeRF.predict() with HOST rays (pinned), H2D + D2H included

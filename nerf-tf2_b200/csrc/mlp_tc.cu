@@ -50,7 +50,7 @@ struct Chunk {
 };
 
 constexpr int kNumJobs = 11;
-constexpr int kDefaultReplicas = 8, kMaxReplicas = 32;
+constexpr int kDefaultReplicas = 1, kMaxReplicas = 32;   // replicas of the image: measured no effect (L2 serves the shared stream fine)
 constexpr int kMaxChunks = 80;
 
 struct ChunkTable {

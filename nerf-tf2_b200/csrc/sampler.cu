@@ -18,6 +18,25 @@ namespace nb {
 
 constexpr int kSamplerWarps = 4;
 
+// Branch-free binary searches over a shared-memory array a[0, n): every lane runs the same log2 steps.
+// upper_bound: #{a[i] <= v};  lower_bound: #{a[i] < v}.  p2 = largest power of two <= n.
+__device__ __forceinline__ int upper_bound_smem(const float* a, int n, int p2, float v) {
+    int pos = 0;
+    for (int step = p2; step > 0; step >>= 1) {
+        const int nxt = pos + step;
+        if (nxt <= n && a[nxt - 1] <= v) pos = nxt;
+    }
+    return pos;
+}
+__device__ __forceinline__ int lower_bound_smem(const float* a, int n, int p2, float v) {
+    int pos = 0;
+    for (int step = p2; step > 0; step >>= 1) {
+        const int nxt = pos + step;
+        if (nxt <= n && a[nxt - 1] < v) pos = nxt;
+    }
+    return pos;
+}
+
 __device__ __forceinline__ void cmpswap(float& a, float& b, bool asc) {
     float lo = fminf(a, b), hi = fmaxf(a, b);
     a = asc ? lo : hi;
@@ -138,15 +157,13 @@ sample_fine_kernel(int64_t B, int Nc, const float* __restrict__ bin_weights, con
     }
 
     // ---- searchsorted(side='right') over cdf[1..Nc-1] + inversion (utils/ray_utils.py:363-376)
+    int p2c = 1;
+    while (p2c * 2 <= Nc) p2c <<= 1;            // largest power of two <= Nc
+    const int p2e = (p2c == Nc) ? (p2c >> 1) : p2c;   // ... and <= Nc - 1 (the inner edges)
     float tf[EF];
 #pragma unroll
     for (int e = 0; e < EF; ++e) {
-        int lo = 0, hi = Nc - 1;  // answer in [0, Nc-1]: number of inner edges <= u
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (s_cdf[1 + mid] <= u[e]) lo = mid + 1; else hi = mid;
-        }
-        int idx = lo;
+        const int idx = upper_bound_smem(s_cdf + 1, Nc - 1, p2e, u[e]);   // number of inner edges <= u, in [0, Nc-1]
         float p = s_pdf[idx];
         float mask = p < 1e-8f ? 0.f : 1.f;
         p = fmaxf(p, 1e-8f);
@@ -168,23 +185,11 @@ sample_fine_kernel(int64_t B, int Nc, const float* __restrict__ bin_weights, con
         __syncwarp();
         // fine element with rank r goes to r + #{coarse < value}
 #pragma unroll
-        for (int e = 0; e < EF; ++e) {
-            int lo = 0, hi = Nc;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (s_tc[mid] < tf[e]) lo = mid + 1; else hi = mid;
-            }
-            s_out[lane * EF + e + lo] = tf[e];
-        }
-        // coarse element k goes to k + #{fine <= value}
+        for (int e = 0; e < EF; ++e) s_out[lane * EF + e + lower_bound_smem(s_tc, Nc, p2c, tf[e])] = tf[e];
+        // coarse element k goes to k + #{fine <= value}   (Nf = 32 EF is a power of two)
         for (int k = lane; k < Nc; k += 32) {
-            float v = s_tc[k];
-            int lo = 0, hi = Nf;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (s_tf[mid] <= v) lo = mid + 1; else hi = mid;
-            }
-            s_out[k + lo] = v;
+            const float v = s_tc[k];
+            s_out[k + upper_bound_smem(s_tf, Nf, Nf, v)] = v;
         }
     } else {
         // generic path: bitonic sort of the padded concat in shared memory
