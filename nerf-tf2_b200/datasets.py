@@ -154,6 +154,7 @@ class Dataset:
         import torch
         from . import ray_utils
         ro, rd, near, far, rgb = [], [], [], [], []
+        c255 = torch.tensor(255.0, device=ray_utils._dev(None), dtype=torch.float32)
         for img, pose, bound, K in zip(data.imgs, data.poses, data.bounds, data.intrinsics):
             H, W = img.shape[:2]
             o, d = ray_utils.get_rays(H, W, K, pose)
@@ -162,7 +163,8 @@ class Dataset:
             rd.append(d)
             near.append(torch.full((n, 1), float(np.float32(bound[0])), device=o.device, dtype=torch.float32))
             far.append(torch.full((n, 1), float(np.float32(bound[1])), device=o.device, dtype=torch.float32))
-            rgb.append(torch.as_tensor(np.ascontiguousarray(img).reshape(-1, 3), device=o.device).to(torch.float32) / 255)
+            # IEEE division like the reference's `rgb / 255` (a tensor divisor: torch turns a scalar one into x * (1/255))
+            rgb.append(torch.as_tensor(np.ascontiguousarray(img).reshape(-1, 3), device=o.device).to(torch.float32) / c255)
         out = RayLevelData(*(torch.cat(x, dim=0) for x in (ro, rd, near, far, rgb)))
         if not on_device:
             out = RayLevelData(*(t.cpu().numpy() for t in out))
