@@ -45,8 +45,10 @@ extern "C" {
 #define NERFB200_COARSE 0
 #define NERFB200_FINE   1
 
-/* Parameters of ONE 8x256 model in Keras creation order (core/model.py:366-387):
- * dense_0..dense_7, sigma, dense_8, dense_9, rgb; each kernel [in,out] row-major then bias. */
+/* Parameters of ONE 8x256 model in the order of Keras' `model.trainable_variables` for the functional
+ * model of core/model.py:334-394 -- layers sorted by decreasing depth from the outputs [rgb, sigma],
+ * ties by output-first traversal -- i.e. dense_0..dense_9, rgb, sigma; each kernel [in,out] row-major
+ * then its bias. Concatenating `model.get_weights()` in order gives exactly this block. */
 #define NERFB200_PARAMS_PER_MODEL 595844
 #define NERFB200_NUM_VARS_PER_MODEL 24
 #define NERFB200_PARAMS_TOTAL (2 * NERFB200_PARAMS_PER_MODEL)  /* coarse then fine */

@@ -40,8 +40,10 @@ extern std::atomic<long long> g_launches;   // kernels launched by this library 
 constexpr int kNumVars = NERFB200_NUM_VARS_PER_MODEL;
 constexpr int kParamsPerModel = NERFB200_PARAMS_PER_MODEL;
 
-// Layer table in Keras creation order (core/model.py:366-387).
-enum Layer { L0 = 0, L1, L2, L3, L4, L5, L6, L7, LSIGMA, L8, L9, LRGB, kNumLayers };
+// Layer table in the order of Keras' `model.layers` / `trainable_variables` for the functional model of
+// core/model.py:334-394: Keras sorts layers by decreasing depth from the outputs [rgb, sigma], ties by the
+// output-first traversal index, which puts the two heads last, rgb before sigma (it is NOT creation order).
+enum Layer { L0 = 0, L1, L2, L3, L4, L5, L6, L7, L8, L9, LRGB, LSIGMA, kNumLayers };
 
 struct LayerDim { int fan_in, fan_out; };
 __host__ __device__ constexpr LayerDim layer_dim(int l) {

@@ -6,7 +6,7 @@ surface (`fit` / `evaluate` / `predict`, `train_step` / `test_step` / `predict_s
 kernels behind the C ABI; torch only owns device memory, streams and the process group.
 
 Parameters are ONE flat fp32 device buffer (coarse model then fine model, variables in Keras
-creation order, kernels [in,out] row-major): the 48 `trainable_variables` are views into it, the
+`model.trainable_variables` order = dense_0..dense_9, rgb, sigma; kernels [in,out] row-major): the 48 `trainable_variables` are views into it, the
 gradient is one flat buffer (a single NCCL all-reduce in data-parallel training)
 and Adam is one fused launch.
 """
@@ -20,7 +20,7 @@ from . import _lib, ops, ray_utils
 from ._lib import BF16, COARSE, FINE, FP16, FP32, PARAMS_PER_MODEL, PARAMS_TOTAL, check, load, ptr, stream_ptr
 from .data import RayDataset
 
-LAYER_NAMES = [f"dense_{i}" for i in range(8)] + ["sigma", "dense_8", "dense_9", "rgb"]
+LAYER_NAMES = [f"dense_{i}" for i in range(10)] + ["rgb", "sigma"]
 LAYER_SHAPES = {
     "dense_0": (63, 256), "dense_1": (256, 256), "dense_2": (256, 256), "dense_3": (256, 256),
     "dense_4": (256, 256), "dense_5": (319, 256), "dense_6": (256, 256), "dense_7": (256, 256),
@@ -104,6 +104,18 @@ class SubModel:
         for v, a in zip(self.trainable_variables, arrays):
             v.assign(a)
         self._nerf._dirty = True
+
+    def save_weights(self, path):
+        """Model.save_weights: Keras `.h5` layout through h5lite, or `.npz` (checkpoint.py)."""
+        from . import checkpoint
+        if path.endswith(".h5") or path.endswith(".hdf5"):
+            checkpoint.save_weights_h5(path, self)
+        else:
+            checkpoint.save_weights(path, self.trainable_variables)
+
+    def load_weights(self, path):
+        from . import checkpoint
+        checkpoint.load_weights(path, self)
 
     def __call__(self, inputs, precision=None):
         xyz, dirs = inputs

@@ -20,8 +20,12 @@ from . import ray_march as rm
 
 F32 = np.float32
 
-LAYER_NAMES = [f"dense_{i}" for i in range(8)] + ["sigma", "dense_8", "dense_9", "rgb"]
-# (fan_in, fan_out) per layer, creation order of get_coarse_or_fine_model (core/model.py:366-387)
+LAYER_NAMES = [f"dense_{i}" for i in range(10)] + ["rgb", "sigma"]
+# Order of Keras' `model.layers` (hence trainable_variables / get_weights / optimizer slots) for the
+# functional model of core/model.py:334-394: Functional._map_graph_network sorts layers by decreasing
+# depth from the outputs [rgb, sigma] and breaks ties by the output-first traversal index, so the two
+# heads come last, rgb before sigma. (TensorFlow is not installable here: restated, not executed.)
+# (fan_in, fan_out) per layer (core/model.py:366-387)
 LAYER_SHAPES = {
     "dense_0": (63, 256), "dense_1": (256, 256), "dense_2": (256, 256), "dense_3": (256, 256),
     "dense_4": (256, 256), "dense_5": (319, 256), "dense_6": (256, 256), "dense_7": (256, 256),
@@ -37,7 +41,7 @@ def variable_names(model_name):
 
 
 def all_variable_names():
-    """nerf.trainable_variables order: coarse then fine, layer creation order."""
+    """nerf.trainable_variables order: coarse then fine, each in LAYER_NAMES order."""
     return variable_names("coarse") + variable_names("fine")
 
 
