@@ -211,6 +211,30 @@ struct RowCtx {
     float dir[3];
 };
 
+// sin/cos of the L octaves of one coordinate for the tensor-core operands. The reference's arguments
+// fl32(x * fl32(2^l pi)) (core/model.py:318-324) are exactly 2^l * a0 with a0 = fl32(x * fl32(pi)) -- scaling by
+// a power of two commutes with rounding -- so an accurate sincosf every 5th octave plus the double-angle
+// identities in between evaluate the SAME arguments with <= ~3e-6 absolute error (2^4 fp32 ulps), three
+// orders of magnitude below the 16-bit rounding the operand gets next (bf16 ulp 3.9e-3, fp16 4.9e-4).
+// The fp32 check path and the standalone posenc kernel keep one sincosf per octave.
+template <int L>
+__device__ __forceinline__ void sincos_octaves(float x, float* e) {
+    const float a0 = __fmul_rn(x, 3.14159274101257324f);
+    float sn = 0.f, cs = 1.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        if (l % 5 == 0) {
+            sincosf(__fmul_rn(a0, (float)(1 << l)), &sn, &cs);
+        } else {
+            const float s2 = __fmul_rn(__fmul_rn(2.f, sn), cs);
+            cs = fmaf(__fmul_rn(-2.f, sn), sn, 1.f);
+            sn = s2;
+        }
+        e[2 * l] = sn;
+        e[2 * l + 1] = cs;
+    }
+}
+
 // Loads the ray of this thread's row, forms xyz = o + t*d (utils/ray_utils.py:251) and writes the
 // L=10 positional encoding (core/model.py:305-332) into the 64-column encoding buffer (col 63 = 0).
 template <bool kHalf>
@@ -218,7 +242,7 @@ __device__ __forceinline__ void prep_tile(const TcParams& p, int tile, int row, 
     rc.grow = (int64_t)tile * kTileRows + row;
     rc.valid = rc.grow < p.R;
     const int64_t lrow = rc.valid ? rc.grow : p.R - 1;
-    const int64_t ray = lrow / p.S;
+    const int64_t ray = (p.R <= 0x7fffffffLL) ? (int64_t)((uint32_t)lrow / (uint32_t)p.S) : lrow / p.S;
     const float tv = __ldg(p.t + lrow);
     float xyz[3];
 #pragma unroll
@@ -229,15 +253,7 @@ __device__ __forceinline__ void prep_tile(const TcParams& p, int tile, int row, 
     float e[64];
     e[0] = xyz[0]; e[1] = xyz[1]; e[2] = xyz[2];
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int l = 0; l < 10; ++l) {
-            float arg = __fmul_rn(xyz[d], __fmul_rn((float)(1 << l), 3.14159274101257324f));
-            float sn, cs;
-            sincosf(arg, &sn, &cs);
-            e[3 + d * 20 + 2 * l] = sn;
-            e[3 + d * 20 + 2 * l + 1] = cs;
-        }
+    for (int d = 0; d < 3; ++d) sincos_octaves<10>(xyz[d], e + 3 + d * 20);
     e[63] = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -257,15 +273,7 @@ __device__ __forceinline__ void write_enc_dir(const float (&dir)[3], uint8_t* en
     float e[32];
     e[0] = dir[0]; e[1] = dir[1]; e[2] = dir[2];
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            float arg = __fmul_rn(dir[d], __fmul_rn((float)(1 << l), 3.14159274101257324f));
-            float sn, cs;
-            sincosf(arg, &sn, &cs);
-            e[3 + d * 8 + 2 * l] = sn;
-            e[3 + d * 8 + 2 * l + 1] = cs;
-        }
+    for (int d = 0; d < 3; ++d) sincos_octaves<4>(dir[d], e + 3 + d * 8);
 #pragma unroll
     for (int i = 27; i < 32; ++i) e[i] = 0.f;
 #pragma unroll
@@ -340,8 +348,8 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_
 
 
 
-// Inference epilogue with packed arithmetic: add.f32x2 for the bias, one cvt per pair, ReLU as max on the
-// packed 16-bit pair (rounding is monotonic and sign preserving, so max(cvt(x), 0) == cvt(max(x, 0))).
+// Inference epilogue with packed arithmetic: add.f32x2 for the bias and ONE conversion per pair with the
+// ReLU folded into it (cvt.rn.relu; rounding is monotonic and sign preserving, so it equals cvt(max(x, 0))).
 template <bool kHalf, int NG, bool kRelu>
 __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const float* s_bias, uint8_t* act, int row) {
     uint32_t r[2][32];
@@ -358,15 +366,8 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
             const float4 bb = b4[i];
             const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1])), make_float2(bb.x, bb.y));
             const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(bb.z, bb.w));
-            if (kHalf) {
-                __half2 h0 = __floats2half2_rn(s0.x, s0.y), h1 = __floats2half2_rn(s1.x, s1.y);
-                if (kRelu) { const __half2 z = __floats2half2_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
-                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
-            } else {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(s0.x, s0.y), h1 = __floats2bfloat162_rn(s1.x, s1.y);
-                if (kRelu) { const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
-                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
-            }
+            if (kRelu) { o[2 * i] = pack2_relu<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2_relu<kHalf>(s1.x, s1.y); }
+            else { o[2 * i] = pack2<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2<kHalf>(s1.x, s1.y); }
         }
         uint8_t* chunk = act + (g >> 1) * 16384;
         const int u0 = (g & 1) * 4;
@@ -837,7 +838,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                         else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row);
                     }
                     if (j == 5) {
+                        long long _td = dbg_on ? clock64() : 0;
                         write_enc_dir<kHalf>(cur.dir, enc, row);
+                        if (dbg_on) dbg_acc2 += (unsigned long long)(clock64() - _td);
                         if (kTrain && tstash) { pendE_dst = tstash + kStashChunkEncDir * 16384; pendE_bytes = 16384; }
                     }
                     if (j == 7) {
@@ -851,7 +854,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     if (j == 9) {
                         const int nq = qd + num_clusters;
                         if (nq < quads && nq * 4 + t * 2 < p.num_tiles) {
+                            long long _tp = dbg_on ? clock64() : 0;
                             prep_tile<kHalf>(p, tile_of(nq), row, enc, nxt);
+                            if (dbg_on) dbg_acc3 += (unsigned long long)(clock64() - _tp);
                             if (kTrain && tile_of(nq) < p.num_tiles) { pendE_dst = p.stash + (size_t)tile_of(nq) * kStashTileBytes + kStashChunkEncXyz * 16384; pendE_bytes = 16384; }
                         }
                     }
@@ -971,15 +976,8 @@ __device__ __forceinline__ void v3_drain_chunk(uint32_t tmem_cols, const float* 
                 sig_acc = fmaf(fmaxf(s1.x, 0.f), w.z, sig_acc);
                 sig_acc = fmaf(fmaxf(s1.y, 0.f), w.w, sig_acc);
             }
-            if (kHalf) {
-                __half2 h0 = __floats2half2_rn(s0.x, s0.y), h1 = __floats2half2_rn(s1.x, s1.y);
-                if (kRelu) { const __half2 z = __floats2half2_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
-                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
-            } else {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(s0.x, s0.y), h1 = __floats2bfloat162_rn(s1.x, s1.y);
-                if (kRelu) { const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f); h0 = __hmax2(h0, z); h1 = __hmax2(h1, z); }
-                o[2 * i] = *reinterpret_cast<uint32_t*>(&h0); o[2 * i + 1] = *reinterpret_cast<uint32_t*>(&h1);
-            }
+            if (kRelu) { o[2 * i] = pack2_relu<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2_relu<kHalf>(s1.x, s1.y); }
+            else { o[2 * i] = pack2<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2<kHalf>(s1.x, s1.y); }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -1335,7 +1333,7 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
         const char* names[4] = {"producer", "mma", "epi0", "epi1"};
         fprintf(stderr, "[tc debug] tiles=%d grid=%d (block 0 cycles)\n", p.num_tiles, grid);
         for (int r = 0; r < 8; ++r)
-            fprintf(stderr, "  cta%d %-8s wait0=%llu wait1/epi=%llu biasbar=%llu prep=%llu total=%llu\n", r / 4, names[r % 4], h[r * 8],
+            fprintf(stderr, "  cta%d %-8s wait0=%llu wait1/epi=%llu encdir=%llu prep=%llu total=%llu\n", r / 4, names[r % 4], h[r * 8],
                     h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
     }
     return 0;

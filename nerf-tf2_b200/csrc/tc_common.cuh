@@ -102,6 +102,15 @@ template <bool kHalf> __device__ __forceinline__ uint32_t pack2(float a, float b
     }
 }
 
+// pack2 with the ReLU folded into the conversion (cvt.rn.relu: negative results become +0): one F2FP
+// instead of F2FP + HMNMX2. The first PTX source operand lands in the upper half.
+template <bool kHalf> __device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+    uint32_t d;
+    if constexpr (kHalf) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+
 // 64-bit UMMA descriptor from its low word (start address >> 4; LBO = 0): the high word is constant
 // (SBO = 1024 B, version 1, SWIZZLE_128B).
 __device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {
