@@ -492,26 +492,112 @@ class NeRF:
         independent, so the result does not depend on the grouping). `return_weights=False` drops
         the per-sample `weights` tensors (0.66 GB per 800x800 view that no reference consumer reads)."""
         group, count = [], 0
-        res_c, res_f = [], []
-        ray0 = 0
+        res_c, res_f = [], []            # per chunk: dict of device tensors, or of pinned host tensors (as_numpy)
+        ray0, chunk_idx = 0, 0
+        pending = []                     # the chunk whose D2H copies are still in flight
+        keep = []                        # device tensors with a D2H copy in flight
+        cur = torch.cuda.current_stream(self.device)
+        cs = self._ws.get("copy_stream")
+        if cs is None:
+            cs = self._ws["copy_stream"] = torch.cuda.Stream(device=self.device)
+
+        def pinned(tag, shape, dtype=torch.float32):
+            """Persistent pinned staging buffers (cudaHostAlloc per call would cost more than the copy)."""
+            key = ("pin", tag, tuple(shape), dtype)
+            buf = self._ws.get(key)
+            if buf is None:
+                buf = self._ws[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            return buf
+
+        def stage_in(cols):
+            """Host batches -> one pinned buffer per ray field (double-buffered) -> device, on the copy stream."""
+            slot = chunk_idx & 1
+            ev = self._ws.get(("in_done", slot))
+            if ev is not None:
+                ev.synchronize()                      # the previous H2D out of this staging slot has finished
+            dev = []
+            cap = -(-count // 65536) * 65536
+            with torch.cuda.stream(cs):
+                for f, col in enumerate(cols):
+                    width = int(np.asarray(col[0]).reshape(col[0].shape[0], -1).shape[1])
+                    pin = pinned(("in", slot, f), (cap, width))
+                    n = 0
+                    view = pin.numpy()
+                    for c in col:
+                        c = np.asarray(c, dtype=np.float32).reshape(c.shape[0], -1)
+                        view[n:n + c.shape[0]] = c
+                        n += c.shape[0]
+                    d = pin[:n].to(self.device, non_blocking=True)
+                    d.record_stream(cur)
+                    dev.append(d)
+                ev = self._ws[("in_done", slot)] = torch.cuda.Event()
+                ev.record(cs)
+            cur.wait_event(ev)
+            return dev
+
+        def stage_out(which, d):
+            """Device results of one chunk -> pinned host buffers, on the copy stream, overlapping the next chunk."""
+            done = torch.cuda.Event()
+            done.record(cur)
+            out = {}
+            with torch.cuda.stream(cs):
+                cs.wait_event(done)
+                for k, v in d.items():
+                    if v.dim() > 1 and v.shape[1] > 4:      # per-sample `weights`: too large to keep pinned copies of
+                        out[k] = v
+                        continue
+                    pin = pinned(("out", which, chunk_idx, k), (-(-v.shape[0] // 65536) * 65536,) + tuple(v.shape[1:]))
+                    pin[:v.shape[0]].copy_(v, non_blocking=True)
+                    v.record_stream(cs)
+                    out[k] = pin[:v.shape[0]]
+                out["_done"] = torch.cuda.Event()
+                out["_done"].record(cs)
+            keep.append(d)
+            return out
+
+        # a plain (non-repeating, unskipped) RayDataset knows its length: results are written in place
+        total = x.n if isinstance(x, RayDataset) and not x._repeat and not x._skip and not x.drop_remainder else None
+        final = [{}, {}]
+
+        def drain(which, out, row0):
+            """Pinned chunk results -> the returned NumPy arrays (host work that overlaps the next chunk on the GPU)."""
+            out.pop("_done").synchronize()
+            res = {}
+            for k, v in out.items():
+                if v.is_cuda:
+                    res[k] = v
+                elif total is not None:
+                    if k not in final[which]:
+                        final[which][k] = np.empty((total,) + tuple(v.shape[1:]), dtype=np.float32)
+                    final[which][k][row0:row0 + v.shape[0]] = v.numpy()
+                else:
+                    res[k] = torch.from_numpy(v.numpy().copy())
+            return res
 
         def flush():
-            nonlocal group, count, ray0
+            nonlocal group, count, ray0, chunk_idx
             if not group:
                 return
             cols = list(zip(*group))
-            dev = []
-            for col in cols:
-                if isinstance(col[0], torch.Tensor) and col[0].is_cuda:
-                    dev.append(torch.cat(col, dim=0) if len(col) > 1 else col[0])
-                else:
-                    host = np.concatenate([np.asarray(c, dtype=np.float32) for c in col], axis=0)
-                    pin = torch.from_numpy(host).pin_memory()
-                    dev.append(pin.to(self.device, non_blocking=True))
-            pc, pf = self.render_rays(dev[0], dev[1], dev[2], dev[3], ray0, need_weights=return_weights)
-            res_c.append(pc)
-            res_f.append(pf)
+            on_dev = isinstance(cols[0][0], torch.Tensor) and cols[0][0].is_cuda
+            if on_dev:
+                dev = [torch.cat(col, dim=0) if len(col) > 1 else col[0] for col in cols]
+            else:
+                dev = stage_in(cols)
+            pc, pf = self.render_rays(dev[0], dev[1], dev[2].reshape(-1, 1), dev[3].reshape(-1, 1), ray0,
+                                      need_weights=return_weights)
+            if as_numpy:
+                pc, pf = stage_out(0, pc), stage_out(1, pf)
+                if pending:                               # the previous chunk's copies, while this one computes
+                    qc, qf, r0 = pending.pop()
+                    res_c.append(drain(0, qc, r0))
+                    res_f.append(drain(1, qf, r0))
+                pending.append((pc, pf, ray0))
+            else:
+                res_c.append(pc)
+                res_f.append(pf)
             ray0 += count
+            chunk_idx += 1
             group, count = [], 0
 
         for batch in x:
@@ -522,15 +608,22 @@ class NeRF:
                 flush()
         flush()
 
-        def finish(ds):
+        if as_numpy and pending:
+            qc, qf, r0 = pending.pop()
+            res_c.append(drain(0, qc, r0))
+            res_f.append(drain(1, qf, r0))
+
+        def finish(which, ds):
             if not ds:
                 return {}
-            out = {k: torch.cat([d[k] for d in ds], dim=0) for k in ds[0]}
-            if as_numpy:
-                out = {k: v.cpu().numpy() for k, v in out.items()}
+            if not as_numpy:
+                return {k: torch.cat([d[k] for d in ds], dim=0) for k in ds[0]}
+            out = dict(final[which])
+            for k in ds[0]:                               # what was not written in place
+                out[k] = np.concatenate([d[k].cpu().numpy() for d in ds], axis=0)
             return out
 
-        return finish(res_c), finish(res_f)
+        return finish(0, res_c), finish(1, res_f)
 
 
 def get_coarse_or_fine_model(model_name, num_units=256, params=None, **kw):
