@@ -318,7 +318,7 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_
             if (mask_row) {   // training: ReLU bitmask of this group for the backward pass
                 uint32_t m = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f) ? (1u << i) : 0u;
+                for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f) ? (1u << mask_bit(i)) : 0u;
                 mask_row[g] = m;
             }
         }
@@ -350,8 +350,10 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_
 
 // Inference epilogue with packed arithmetic: add.f32x2 for the bias and ONE conversion per pair with the
 // ReLU folded into it (cvt.rn.relu; rounding is monotonic and sign preserving, so it equals cvt(max(x, 0))).
-template <bool kHalf, int NG, bool kRelu>
-__device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const float* s_bias, uint8_t* act, int row) {
+template <bool kHalf, int NG, bool kRelu, bool kSigma = false>
+__device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const float* s_bias, uint8_t* act, int row,
+                                                     uint32_t* mask_row = nullptr, const float4* ws4 = nullptr,
+                                                     float* sig_acc = nullptr) {
     uint32_t r[2][32];
     tmem_ld32(tmem_row, r[0]);
 #pragma unroll
@@ -366,8 +368,23 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
             const float4 bb = b4[i];
             const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1])), make_float2(bb.x, bb.y));
             const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(bb.z, bb.w));
+            if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
+                const float4 w = __ldg(ws4 + 8 * g + i);
+                float acc = *sig_acc;
+                acc = fmaf(fmaxf(s0.x, 0.f), w.x, acc);
+                acc = fmaf(fmaxf(s0.y, 0.f), w.y, acc);
+                acc = fmaf(fmaxf(s1.x, 0.f), w.z, acc);
+                acc = fmaf(fmaxf(s1.y, 0.f), w.w, acc);
+                *sig_acc = acc;
+            }
             if (kRelu) { o[2 * i] = pack2_relu<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2_relu<kHalf>(s1.x, s1.y); }
             else { o[2 * i] = pack2<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2<kHalf>(s1.x, s1.y); }
+        }
+        if (kRelu && mask_row) {   // training: ReLU bitmask from the packed outputs (layout: mask_bit(), tc_layout.cuh)
+            uint32_t m = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m |= pos_mask2<kHalf>(o[k]) & (0x00010001u << k);
+            mask_row[g] = m;
         }
         uint8_t* chunk = act + (g >> 1) * 16384;
         const int u0 = (g & 1) * 4;
@@ -823,16 +840,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     if (kTrain) {
                         uint32_t* mrow = nullptr;
                         if (tstash && j != 8) mrow = reinterpret_cast<uint32_t*>(tstash + kStashMaskOfs) + ((j == 9 ? 8 : j) * 128 + row) * 8;
-                        if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
-                        else if (j == 8) epilogue_cols<kHalf, 8, false, false>(tmem_row, s_bias, act, row, ws4, sig_acc);
-                        else if (j == 9) epilogue_cols<kHalf, 4, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
-                        else epilogue_cols<kHalf, 8, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
+                        if (j == 7) epilogue_cols_packed<kHalf, 8, true, true>(tmem_row, s_bias, act, row, mrow, ws4, &sig_acc);
+                        else if (j == 8) epilogue_cols_packed<kHalf, 8, false>(tmem_row, s_bias, act, row);
+                        else if (j == 9) epilogue_cols_packed<kHalf, 4, true>(tmem_row, s_bias, act, row, mrow);
+                        else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row, mrow);
                         if (tstash) {
                             pendA_dst = tstash + (j < 8 ? stash_chunk_Y(j) : j == 8 ? kStashChunkBott : kStashChunkY9) * 16384;
                             pendA_bytes = j == 9 ? 2 * 16384 : 4 * 16384;
                         }
                     } else {
-                        if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc);
+                        if (j == 7) epilogue_cols_packed<kHalf, 8, true, true>(tmem_row, s_bias, act, row, nullptr, ws4, &sig_acc);
                         else if (j == 8) epilogue_cols_packed<kHalf, 8, false>(tmem_row, s_bias, act, row);
                         else if (j == 9) epilogue_cols_packed<kHalf, 4, true>(tmem_row, s_bias, act, row);
                         else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row);

@@ -131,7 +131,7 @@ __device__ __forceinline__ void bwd_epilogue_cols(uint32_t tmem_row, uint8_t* ac
         if (kMask) {
             const uint32_t m = valid ? mask[g] : 0u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (m >> i) & 1u ? v[i] : 0.f;
+            for (int i = 0; i < 32; ++i) v[i] = (m >> mask_bit(i)) & 1u ? v[i] : 0.f;
         } else if (!valid) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kBThreads, 1) bwd_data_kernel(const BwdParams 
                     for (int i = 0; i < 32; ++i) {
                         const int c = 32 * g + i;
                         float a = dzr[0] * __ldg(Wrgb + 3 * c) + dzr[1] * __ldg(Wrgb + 3 * c + 1) + dzr[2] * __ldg(Wrgb + 3 * c + 2);
-                        v[i] = (m >> i) & 1u ? a : 0.f;
+                        v[i] = (m >> mask_bit(i)) & 1u ? a : 0.f;
                     }
                     uint8_t* chunk = act + (g >> 1) * kChunkBytes;
                     const int u0 = (g & 1) * 4;
@@ -515,7 +515,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBThreads, 1) bwd_da
                     for (int i = 0; i < 32; ++i) {
                         const int c = 32 * g + i;
                         float a = dzr[0] * __ldg(Wrgb + 3 * c) + dzr[1] * __ldg(Wrgb + 3 * c + 1) + dzr[2] * __ldg(Wrgb + 3 * c + 2);
-                        v[i] = (m >> i) & 1u ? a : 0.f;
+                        v[i] = (m >> mask_bit(i)) & 1u ? a : 0.f;
                     }
                     uint8_t* chunk = act + (g >> 1) * kChunkBytes;
                     const int u0 = (g & 1) * 4;

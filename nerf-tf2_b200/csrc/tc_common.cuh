@@ -111,6 +111,17 @@ template <bool kHalf> __device__ __forceinline__ uint32_t pack2_relu(float a, fl
     return d;
 }
 
+// 0xFFFF in each half of the word whose 16-bit value is > 0 (one HSET2-class instruction).
+template <bool kHalf> __device__ __forceinline__ uint32_t pos_mask2(uint32_t packed) {
+    if constexpr (kHalf) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&packed);
+        return __hgt2_mask(h, __floats2half2_rn(0.f, 0.f));
+    } else {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&packed);
+        return __hgt2_mask(h, __floats2bfloat162_rn(0.f, 0.f));
+    }
+}
+
 // 64-bit UMMA descriptor from its low word (start address >> 4; LBO = 0): the high word is constant
 // (SBO = 1024 B, version 1, SWIZZLE_128B).
 __device__ __forceinline__ uint64_t umma_desc_from_lo(uint32_t lo) {

@@ -19,6 +19,10 @@ constexpr int kStashChunkY9 = 38;                                     // post-Re
 constexpr int kStashChunks = 40;
 constexpr int kStashMaskLayers = 9;                                   // ReLU bitmasks: Y0..Y7 -> 0..7, Y9 -> 8
 constexpr int kStashMaskOfs = kStashChunks * 16384;                   // [layer][row][8 x u32]
+// ReLU bitmask word of a 32-column group: column i of the group lives at bit mask_bit(i) -- even columns in
+// bits 0..15, odd columns in bits 16..31 -- so that the forward epilogue builds it from the packed 16-bit
+// pairs with one compare + one LOP3 per pair (word k = columns 2k, 2k+1 -> bits k and 16+k).
+__host__ __device__ constexpr int mask_bit(int i) { return ((i & 1) << 4) | (i >> 1); }
 constexpr int kStashOutOfs = kStashMaskOfs + kStashMaskLayers * 128 * 32;   // rgb[128][3] fp32, then sigma[128] fp32
 constexpr int kStashTileBytes = kStashOutOfs + 128 * 16;
 static_assert(kStashTileBytes % 16 == 0, "tile stash must keep 16-byte alignment");
