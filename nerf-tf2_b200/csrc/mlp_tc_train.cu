@@ -604,17 +604,23 @@ static void build_dw_jobs(DwJob* j) {
 constexpr int kDwStageRows = 64;                       // rows (= UMMA K) per pipeline stage: 4 K-steps of 16
 constexpr int kDwHalfChunk = kChunkBytes / 2;          // 64 rows of a chunk image = 8 KB
 constexpr int kDwStageBytes = 8 * kDwHalfChunk;        // up to 4 X half-chunks + 4 dZ half-chunks = 64 KB
-constexpr int kDwStages = 3;
-constexpr int kDwSmemBar = kDwStages * kDwStageBytes;  // 192 KB
-constexpr int kDwSmemBias = kDwSmemBar + 128;          // 256 fp32 column sums
-constexpr int kDwSmemTotal = kDwSmemBias + 1024;
+constexpr int kDwRingBytes = 3 * kDwStageBytes;        // 192 KB ring: 3 stages of a full job, up to 8 of a small one --
+constexpr int kDwMaxStages = 8;                        // the bytes in flight per CTA, not the stage count, are constant
+constexpr int kDwSmemBar = kDwRingBytes;
+constexpr int kDwSmemBias = kDwSmemBar + 256;          // 256 fp32 column sums
+constexpr int kDwSmemTotal = kDwSmemBias + 4096;          // [4][256] fp32 column sums
 constexpr int kDwThreads = 192;                        // warps 0-3: bias + flush, warp 4: producer, warp 5: MMA
 
+// ONE launch runs all 14 jobs of a model side by side: job j owns CTAs [cta0[j], cta0[j+1]) (its K-split,
+// sized in proportion to the bytes the job streams), so the 148 CTAs produce 148 accumulator dumps per model
+// instead of 148 per job, and one reduce launch folds them.
 struct DwParams {
-    DwJob job;
+    DwJob job[kDwJobs];
+    int cta0[kDwJobs + 1];
+    long long poff[kDwJobs];     // float offset of job j's accumulator dumps: [split][mblocks*128][N]
+    long long boff[kDwJobs];     // float offset of job j's bias column sums: [split][256]
     const uint8_t* stash; const uint8_t* gstash;
-    float* partial;          // [grid][mblocks*128][N] fp32 accumulator dump (only the region this job produces)
-    float* bias_partial;     // [grid][256]
+    float* partial;
     int num_tiles;
 };
 
@@ -632,17 +638,23 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t sbar = sbase + kDwSmemBar;   // full[3], empty[3], done
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kDwSmemBar + 8 * 8);
-    float* s_bias = reinterpret_cast<float*>(smem + kDwSmemBias);
-    const DwJob jb = p.job;
+    const uint32_t sbar = sbase + kDwSmemBar;   // full[8], empty[8], done
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kDwSmemBar + 8 * (2 * kDwMaxStages + 1));
+    int jidx = 0;
+    while (jidx + 1 < kDwJobs && (int)blockIdx.x >= p.cta0[jidx + 1]) ++jidx;
+    const DwJob jb = p.job[jidx];
+    const int split = (int)blockIdx.x - p.cta0[jidx], nsplit = p.cta0[jidx + 1] - p.cta0[jidx];
     const int xn = jb.x_nchunks == 1 ? 2 : jb.x_nchunks;      // a single X chunk is loaded twice to fill M = 128
     const int mblocks = xn / 2;
     const int N = jb.dz_nchunks * 64;
-    const uint32_t stage_tx = (uint32_t)(xn + jb.dz_nchunks) * kDwHalfChunk;
+    const uint32_t stage_tx = (uint32_t)(xn + jb.dz_nchunks) * kDwHalfChunk;     // = the stage stride in the ring
+    const int ring = min(kDwMaxStages, kDwRingBytes / (int)stage_tx);
+    auto full_bar = [&](uint32_t s) { return sbar + 8 * s; };
+    auto empty_bar = [&](uint32_t s) { return sbar + 8 * (kDwMaxStages + s); };
+    const uint32_t done_bar = sbar + 8 * (2 * kDwMaxStages);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kDwStages; ++s) { mbar_init(sbar + 8 * s, 1); mbar_init(sbar + 8 * (kDwStages + s), 1 + 4); }
-        mbar_init(sbar + 8 * 6, 1);
+        for (int s = 0; s < kDwMaxStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1 + 4); }
+        mbar_init(done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -653,7 +665,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int my_tiles = split < p.num_tiles ? (p.num_tiles - 1 - split) / nsplit + 1 : 0;
     const int nstages = my_tiles * 2;           // two 64-row stages per tile
     constexpr int fmt = kHalf ? 0 : 1;
 
@@ -661,18 +673,18 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < nstages; ++it) {
-                const int tile = blockIdx.x + (it >> 1) * gridDim.x;
+                const int tile = split + (it >> 1) * nsplit;
                 const uint32_t half = (uint32_t)(it & 1) * kDwHalfChunk;
                 const uint8_t* xs = p.stash + (size_t)tile * kStashTileBytes + (size_t)jb.x_chunk0 * kChunkBytes + half;
                 const uint8_t* zs = p.gstash + (size_t)tile * kGradTileBytes + (size_t)jb.dz_chunk0 * kChunkBytes + half;
-                mbar_wait(sbar + 8 * (kDwStages + stage), phase ^ 1);
-                mbar_expect_tx(sbar + 8 * stage, stage_tx);
-                const uint32_t dst = sbase + stage * kDwStageBytes;
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                mbar_expect_tx(full_bar(stage), stage_tx);
+                const uint32_t dst = sbase + stage * stage_tx;
                 for (int c = 0; c < xn; ++c)
-                    bulk_g2s(dst + c * kDwHalfChunk, xs + (size_t)(jb.x_nchunks == 1 ? 0 : c) * kChunkBytes, kDwHalfChunk, sbar + 8 * stage);
+                    bulk_g2s(dst + c * kDwHalfChunk, xs + (size_t)(jb.x_nchunks == 1 ? 0 : c) * kChunkBytes, kDwHalfChunk, full_bar(stage));
                 for (int c = 0; c < jb.dz_nchunks; ++c)
-                    bulk_g2s(dst + (4 + c) * kDwHalfChunk, zs + (size_t)c * kChunkBytes, kDwHalfChunk, sbar + 8 * stage);
-                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+                    bulk_g2s(dst + (xn + c) * kDwHalfChunk, zs + (size_t)c * kChunkBytes, kDwHalfChunk, full_bar(stage));
+                if (++stage == (uint32_t)ring) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 5) {
@@ -680,9 +692,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
             const uint32_t idesc = umma_idesc_mn(fmt, N);
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < nstages; ++it) {
-                mbar_wait(sbar + 8 * stage, phase);
+                mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t xb = sbase + stage * kDwStageBytes, zb = xb + 4 * kDwHalfChunk;
+                const uint32_t xb = sbase + stage * stage_tx, zb = xb + xn * kDwHalfChunk;
                 if (elect_one_sync()) {
 #pragma unroll 1
                     for (int mb = 0; mb < mblocks; ++mb) {
@@ -694,52 +706,65 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
                             umma_f16(tmem_base + (uint32_t)(mb * 256), ad, bd, idesc, (it == 0 && k == 0) ? 0u : 1u);
                         }
                     }
-                    umma_commit(sbar + 8 * (kDwStages + stage));
-                    if (it == nstages - 1) umma_commit(sbar + 8 * 6);
+                    umma_commit(empty_bar(stage));
+                    if (it == nstages - 1) umma_commit(done_bar);
                 }
                 __syncwarp();
-                if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+                if (++stage == (uint32_t)ring) { stage = 0; phase ^= 1; }
             }
         }
     } else {
-        // ---- warps 0-3: bias gradient = column sums of dZ over this CTA's rows, read from the same smem stages
-        const int tid = threadIdx.x;             // 0..127 -> columns tid and tid + 128
-        float s0 = 0.f, s1 = 0.f;
+        // ---- warps 0-3: bias gradient = column sums of dZ over this CTA's rows, read from the same smem stages.
+        // Thread = one 16-byte unit (8 columns) x every 4th row: 16 LDS.128 per stage instead of 128 scalar loads
+        // (the scalar version made this the slowest role of the CTA and capped the kernel at ~60 % of HBM).
+        const int tid = threadIdx.x;             // 0..127
+        const int unit = tid & 31, rg = tid >> 5;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         uint32_t stage = 0, phase = 0;
         const bool want_bias = jb.bias_layer >= 0;
+        const bool my_cols = want_bias && unit * 8 < N;
         for (int it = 0; it < nstages; ++it) {
-            mbar_wait(sbar + 8 * stage, phase);
-            if (want_bias) {
-                const uint8_t* zb = smem + stage * kDwStageBytes + 4 * kDwHalfChunk;
+            mbar_wait(full_bar(stage), phase);
+            if (my_cols) {
+                const uint8_t* zb = smem + stage * stage_tx + xn * kDwHalfChunk + (unit >> 3) * kDwHalfChunk;
 #pragma unroll 4
-                for (int r = 0; r < kDwStageRows; ++r) {
+                for (int r = rg; r < kDwStageRows; r += 4) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(zb + r * 128 + (((unit & 7) ^ (r & 7)) << 4));
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = tid + 128 * h;
-                        if (col < N) {
-                            const uint8_t* cz = zb + (col >> 6) * kDwHalfChunk + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
-                            float v;
-                            if (kHalf) v = __half2float(*reinterpret_cast<const __half*>(cz));
-                            else v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cz));
-                            if (h == 0) s0 += v; else s1 += v;
+                    for (int i = 0; i < 4; ++i) {
+                        float lo, hi;
+                        if (kHalf) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                            lo = f.x; hi = f.y;
+                        } else {
+                            lo = __uint_as_float(w[i] << 16); hi = __uint_as_float(w[i] & 0xFFFF0000u);
                         }
+                        acc[2 * i] += lo;
+                        acc[2 * i + 1] += hi;
                     }
                 }
             }
-            if (lane == 0) mbar_arrive(sbar + 8 * (kDwStages + stage));     // one arrive per warp (count 1 + 4)
+            if (lane == 0) mbar_arrive(empty_bar(stage));     // one arrive per warp (count 1 + 4)
             __syncwarp();
-            if (++stage == kDwStages) { stage = 0; phase ^= 1; }
+            if (++stage == (uint32_t)ring) { stage = 0; phase ^= 1; }
         }
         if (want_bias) {
-            p.bias_partial[(size_t)blockIdx.x * 256 + tid] = s0;
-            p.bias_partial[(size_t)blockIdx.x * 256 + tid + 128] = s1;
+            // fold the 4 row groups (one per warp) in a fixed order
+            float* s_red = reinterpret_cast<float*>(smem + kDwSmemBias);      // [4][256]
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s_red[rg * 256 + unit * 8 + i] = acc[i];
+            named_bar_sync(1, 128);
+            float* bp = p.partial + p.boff[jidx] + (size_t)split * 256;
+            for (int c = tid; c < 256; c += 128)
+                bp[c] = c < N ? (s_red[c] + s_red[256 + c]) + (s_red[512 + c] + s_red[768 + c]) : 0.f;
         }
         // ---- flush the accumulators: thread = TMEM lane = X feature within the M-block
         if (nstages > 0) {
-            mbar_wait(sbar + 8 * 6, 0);
+            mbar_wait(done_bar, 0);
             tc_fence_after();
         }
-        float* dst = p.partial + (size_t)blockIdx.x * (size_t)(mblocks * 128) * N;
+        float* dst = p.partial + p.poff[jidx] + (size_t)split * (size_t)(mblocks * 128) * N;
         for (int mb = 0; mb < mblocks; ++mb) {
             float* drow = dst + ((size_t)mb * 128 + warp * 32 + lane) * N;
             for (int c0 = 0; c0 < N; c0 += 32) {
@@ -762,25 +787,33 @@ __global__ void __launch_bounds__(kDwThreads, 1) dw_kernel(const DwParams p) {
     if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-// 3. reduce the per-CTA partials of one job into the flat gradient buffer (+=)
-__global__ void reduce_grads_kernel(DwJob jb, int grid, const float* __restrict__ partial, const float* __restrict__ bias_partial,
-                                    float* __restrict__ G /* one model */) {
+// 3. fold the accumulator dumps of all jobs into the flat gradient buffer (+=): blockIdx.y = job, a fixed
+// summation order over the job's K-splits (deterministic)
+struct ReduceParams {
+    DwJob job[kDwJobs];
+    int nsplit[kDwJobs];
+    long long poff[kDwJobs], boff[kDwJobs];
+};
+__global__ void reduce_grads_kernel(const ReduceParams rp, const float* __restrict__ partial, float* __restrict__ G /* one model */) {
+    const DwJob jb = rp.job[blockIdx.y];
+    const int nsplit = rp.nsplit[blockIdx.y];
     const int fan_out = layer_dim(jb.layer).fan_out;
     const int total = jb.k_rows * jb.n_cols;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int xn = jb.x_nchunks == 1 ? 2 : jb.x_nchunks;
     const int N = jb.dz_nchunks * 64;
     const size_t per_cta = (size_t)(xn / 2) * 128 * N;
     if (i < total) {
         const int m = i / jb.n_cols, n = i - m * jb.n_cols;
-        const size_t src = (size_t)m * N + jb.n_col0 + n;
+        const float* src = partial + rp.poff[blockIdx.y] + (size_t)m * N + jb.n_col0 + n;
         float s = 0.f;
-        for (int c = 0; c < grid; ++c) s += partial[(size_t)c * per_cta + src];
+        for (int c = 0; c < nsplit; ++c) s += src[(size_t)c * per_cta];
         G[kernel_offset(jb.layer) + (size_t)(jb.k_row0 + m) * fan_out + n] += s;
     } else if (jb.bias_layer >= 0 && i < total + jb.n_cols) {
         const int n = i - total;
+        const float* src = partial + rp.boff[blockIdx.y] + jb.n_col0 + n;
         float s = 0.f;
-        for (int c = 0; c < grid; ++c) s += bias_partial[(size_t)c * 256 + jb.n_col0 + n];
+        for (int c = 0; c < nsplit; ++c) s += src[(size_t)c * 256];
         G[bias_offset(jb.bias_layer) + n] += s;
     }
 }
@@ -832,12 +865,39 @@ static inline int64_t tiles_of(int64_t R) { return (R + kTileRows - 1) / kTileRo
 
 int64_t tc_stash_bytes(int64_t R) { return tiles_of(R) * (int64_t)kStashTileBytes; }
 
-// backward workspace: gradient stash + per-CTA accumulator dumps for the 14 dW jobs
-static int64_t dw_partial_floats(int grid) { return (int64_t)grid * 512 * 256; }
+// backward workspace: gradient stash + one accumulator dump (<= 256 x 256 fp32) and 256 bias sums per CTA
+static int64_t dw_partial_floats(int grid) { return (int64_t)grid * (256 * 256 + 256); }
 int64_t tc_workspace_bytes(int64_t R, int training) {
     if (!training) return 0;
-    const int grid = num_sms();
-    return tiles_of(R) * (int64_t)kGradTileBytes + kDwJobs * (dw_partial_floats(grid) + (int64_t)grid * 256) * 4;
+    const int grid = num_sms() > kDwJobs ? num_sms() : kDwJobs;
+    return tiles_of(R) * (int64_t)kGradTileBytes + dw_partial_floats(grid) * 4;
+}
+
+// K-split sizes: every job gets one CTA, the rest go one at a time to the job with the most bytes per CTA
+static void plan_dw(const DwJob* jobs, int grid, DwParams& dp, ReduceParams& rp) {
+    int cost[kDwJobs], nsplit[kDwJobs];
+    for (int j = 0; j < kDwJobs; ++j) {
+        cost[j] = (jobs[j].x_nchunks == 1 ? 2 : jobs[j].x_nchunks) + jobs[j].dz_nchunks;
+        nsplit[j] = 1;
+    }
+    for (int c = kDwJobs; c < grid; ++c) {
+        int best = 0;
+        for (int j = 1; j < kDwJobs; ++j)
+            if ((long long)cost[j] * nsplit[best] > (long long)cost[best] * nsplit[j]) best = j;
+        ++nsplit[best];
+    }
+    long long off = 0;
+    dp.cta0[0] = 0;
+    for (int j = 0; j < kDwJobs; ++j) {
+        const int xn = jobs[j].x_nchunks == 1 ? 2 : jobs[j].x_nchunks;
+        dp.job[j] = rp.job[j] = jobs[j];
+        rp.nsplit[j] = nsplit[j];
+        dp.cta0[j + 1] = dp.cta0[j] + nsplit[j];
+        dp.poff[j] = rp.poff[j] = off;
+        off += (long long)nsplit[j] * (xn / 2) * 128 * jobs[j].dz_nchunks * 64;
+        dp.boff[j] = rp.boff[j] = off;
+        off += (long long)nsplit[j] * 256;
+    }
 }
 
 int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
@@ -873,19 +933,16 @@ int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const 
 
     DwJob jobs[kDwJobs];
     build_dw_jobs(jobs);
-    const int dgrid = num_tiles < sms ? num_tiles : sms;
-    for (int j = 0; j < kDwJobs; ++j) {
-        DwParams dp;
-        dp.job = jobs[j]; dp.stash = (const uint8_t*)stash; dp.gstash = gstash; dp.num_tiles = num_tiles;
-        dp.partial = partial0 + (size_t)j * (dw_partial_floats(dgrid) + (size_t)dgrid * 256);
-        dp.bias_partial = dp.partial + dw_partial_floats(dgrid);
-        if (half) dw_kernel<true><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
-        else dw_kernel<false><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
-        NB_LAUNCH_CHECK();
-        const int total = jobs[j].k_rows * jobs[j].n_cols + jobs[j].n_cols;
-        reduce_grads_kernel<<<(total + 255) / 256, 256, 0, st>>>(jobs[j], dgrid, dp.partial, dp.bias_partial, G);
-        NB_LAUNCH_CHECK();
-    }
+    const int dgrid = sms > kDwJobs ? sms : kDwJobs;
+    DwParams dp;
+    ReduceParams rp;
+    plan_dw(jobs, dgrid, dp, rp);
+    dp.stash = (const uint8_t*)stash; dp.gstash = gstash; dp.partial = partial0; dp.num_tiles = num_tiles;
+    if (half) dw_kernel<true><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
+    else dw_kernel<false><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
+    NB_LAUNCH_CHECK();
+    reduce_grads_kernel<<<dim3((256 * 256 + 256 + 255) / 256, kDwJobs), 256, 0, st>>>(rp, partial0, G);
+    NB_LAUNCH_CHECK();
     return 0;
 }
 
