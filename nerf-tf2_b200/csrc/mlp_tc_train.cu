@@ -8,13 +8,14 @@
 //     sigma heads (N = 3 and 1) are fp32 CUDA-core work in the prologue/epilogue. Every dZ_l leaves as
 //     a chunk image (tc_layout.cuh) for kernel 2. No dX for the network inputs: sample positions are
 //     constants for autodiff (stop_gradient, utils/ray_utils.py:377).
-//  2. dw_kernel        -- dW_l = X_l^T . dZ_l, a reduction over ALL rows: each CTA walks its share of the
-//     tiles, bulk-loads the X_l and dZ_l chunk images and feeds them to the tensor core as MN-major
-//     operands (K = rows); the [K_in x N_out] fp32 accumulator lives in TMEM for the whole pass and is
-//     flushed once per CTA. Bias gradients (column sums of dZ_l) are accumulated by the otherwise idle
-//     warps from the same shared-memory tiles.
-//  3. reduce_grads_kernel -- sums the per-CTA partials into the flat fp32 gradient buffer (Keras kernel
-//     layout [in,out]).
+//  2. dw_kernel        -- dW_l = X_l^T . dZ_l, a reduction over ALL rows. One launch runs the 14 jobs of a
+//     model side by side (job j owns a K-split of CTAs proportional to the bytes it streams); a CTA walks
+//     its share of the tiles, bulk-loads the X_l and dZ_l chunk images and feeds them to the tensor core as
+//     MN-major operands (K = rows); the [K_in x N_out] fp32 accumulator lives in TMEM for the whole pass
+//     and is flushed once per CTA. Bias gradients (column sums of dZ_l) are accumulated by the otherwise
+//     idle warps from the same shared-memory tiles. HBM bound (95 % of the measured peak).
+//  3. reduce_grads_kernel -- one launch folds the per-CTA dumps of every job, in a fixed order, into the
+//     flat fp32 gradient buffer (Keras kernel layout [in,out]).
 #include "common.cuh"
 #include "mlp.cuh"
 #include "tc_common.cuh"
