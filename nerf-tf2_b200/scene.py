@@ -60,3 +60,36 @@ class SyntheticScene:
 
     def __len__(self):
         return len(self.poses)
+
+
+# Analytic ground truth for end-to-end runs (there are no dataset files offline): a handful of shaded,
+# coloured spheres on a white background, ray traced in NumPy from any camera->W3 pose.
+SPHERES = np.array([   # cx, cy, cz, radius, r, g, b   (W3 units: the scene lives in [-0.5, 0.5]^3)
+    [0.00, 0.00, 0.00, 0.130, 0.85, 0.20, 0.15],
+    [0.18, 0.06, 0.03, 0.075, 0.15, 0.55, 0.85],
+    [-0.15, 0.12, -0.06, 0.085, 0.20, 0.75, 0.25],
+    [0.03, -0.18, 0.07, 0.060, 0.90, 0.80, 0.10],
+], dtype=np.float64)
+
+
+def render_spheres(H, W, K, c2w, spheres=SPHERES, light=(0.3, 0.5, 0.8)):
+    """uint8 [H,W,3] image of the sphere scene seen through pinhole K from pose c2w (pixel (u,v) ->
+    direction ((u-cx)/fx, (v-cy)/fy, 1) like get_rays, utils/ray_utils.py:6-51)."""
+    u, v = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64), indexing="xy")
+    d = np.stack([(u - K[0, 2]) / K[0, 0], (v - K[1, 2]) / K[1, 1], np.ones_like(u)], axis=-1).reshape(-1, 3)
+    d = _normalize(d @ c2w[:3, :3].T)
+    o = c2w[:3, 3]
+    L = _normalize(np.asarray(light, dtype=np.float64))
+    best_t = np.full(d.shape[0], np.inf)
+    rgb = np.ones((d.shape[0], 3))
+    for cx, cy, cz, r, cr, cg, cb in spheres:
+        oc = o - np.array([cx, cy, cz])
+        b = d @ oc
+        disc = b * b - (oc @ oc - r * r)
+        t = -b - np.sqrt(np.maximum(disc, 0.0))
+        hit = (disc > 0) & (t > 0) & (t < best_t)
+        n = _normalize((o + t[:, None] * d) - np.array([cx, cy, cz]))
+        shade = 0.35 + 0.65 * np.maximum(n @ L, 0.0)
+        rgb[hit] = (np.array([cr, cg, cb])[None, :] * shade[:, None])[hit]
+        best_t = np.where(hit, t, best_t)
+    return np.clip(rgb * 255.0 + 0.5, 0, 255).astype(np.uint8).reshape(H, W, 3)
