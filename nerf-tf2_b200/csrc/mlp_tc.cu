@@ -53,10 +53,12 @@ constexpr int kNumJobs = 11;
 constexpr int kDefaultReplicas = 1, kMaxReplicas = 32;   // replicas of the image: measured no effect (L2 serves the shared stream fine)
 constexpr int kMaxChunks = 80;
 
+constexpr uint32_t kBiasTileBytes = 2048;   // one CTA's share of a layer's bias as a tensor-core B operand (see pack_bias_tiles_kernel)
 struct ChunkTable {
     Chunk c[kMaxChunks];
     int n;
     int job_begin[kNumJobs + 1];
+    uint32_t bias_ofs;       // byte offset of the bias tiles [job][cta rank][kBiasTileBytes] behind the weight chunks
     uint32_t bytes;
 };
 
@@ -91,7 +93,8 @@ static ChunkTable build_chunk_table() {
     }
     t.job_begin[kNumJobs] = n;
     t.n = n;
-    t.bytes = ofs;
+    t.bias_ofs = ofs;
+    t.bytes = ofs + kNumJobs * 2 * kBiasTileBytes;
     return t;
 }
 
@@ -156,6 +159,32 @@ __global__ void pack_weights_kernel(const float* __restrict__ P /* one model */,
     *reinterpret_cast<uint4*>(img + byte) = *reinterpret_cast<uint4*>(vals);
 }
 
+// The layer bias as a tensor-core operand (pair kernel): the first MMA of every layer multiplies a "ones" A operand
+// (columns k = 0, 1 are 1.0, the rest 0; see the kernel) with this B tile and starts the accumulator at the bias, so
+// the epilogue neither loads nor adds it (the broadcast shared-memory loads of the bias were ~1000 of its ~1800
+// cycles per layer: as many bytes into registers as the accumulator itself; tools/epi_probe.cu). K-major, no swizzle:
+// N-row i of the CTA's share is the 16 bytes [hi, lo, 0, 0, 0, 0, 0, 0] with hi + lo = bias to ~2^-17 relative.
+template <typename T>
+__global__ void pack_bias_tiles_kernel(const float* __restrict__ P /* one model */, uint8_t* __restrict__ tiles) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (job, rank, row)
+    if (i >= kNumJobs * 2 * 128) return;
+    const int job = i / 256, rank = (i >> 7) & 1, row = i & 127;
+    const int job_layer[kNumJobs] = {L0, L1, L2, L3, L4, L5, L6, L7, L8, L9, LRGB};
+    const int l = job_layer[job];
+    const int N = job < 9 ? 256 : (job == 9 ? 128 : 16);
+    const int rows = N / 2;                                        // N-rows this CTA supplies
+    T v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = to16<T>(0.f);
+    const int n = rank * rows + row;
+    if (row < rows && n < layer_dim(l).fan_out) {
+        const float b = P[bias_offset(l) + n];
+        v[0] = to16<T>(b);
+        v[1] = to16<T>(b - (float)v[0]);
+    }
+    *reinterpret_cast<uint4*>(tiles + (size_t)(job * 2 + rank) * kBiasTileBytes + row * 16) = *reinterpret_cast<uint4*>(v);
+}
+
 __global__ void pack_heads_kernel(const float* __restrict__ P, float* __restrict__ hp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= HeadOffsets::total) return;
@@ -183,8 +212,10 @@ constexpr int kSmemAct = 0;
 constexpr int kSmemEnc = kSmemAct + 2 * kActBytes;
 constexpr int kSmemRing = kSmemEnc + 2 * kEncBytes;
 constexpr int kSmemBar = kSmemRing + kStages * kStageBytes;
-constexpr int kSmemBias = kSmemBar + 256;             // 2 slots x 256 fp32
-constexpr int kSmemTotal = kSmemBias + 2 * 1024;
+constexpr int kSmemBias = kSmemBar + 256;             // single-CTA kernel: 2 slots x 256 fp32 bias staging
+constexpr int kSmemOnes = kSmemBias;                  // pair kernel: 256 B "ones" A operand + one 2 KB bias tile instead
+constexpr int kSmemBiasTile = kSmemOnes + 256;
+constexpr int kSmemTotal = kSmemBiasTile + 2048;
 static_assert(kSmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 constexpr int kThreads = 320;
 constexpr int kProducerWarp = 8, kMmaWarp = 9;   // highest warp ids: the per-SMSP arbiter favours high warp ids,
@@ -193,6 +224,7 @@ constexpr int kProducerWarp = 8, kMmaWarp = 9;   // highest warp ids: the per-SM
 struct TcParams {
     const uint8_t* wimg;     // packed weights of this model/precision (replica 0)
     uint32_t wimg_stride;    // bytes between replicas
+    uint32_t bias_ofs;       // byte offset of the bias tiles inside the image
     int replicas;            // CTAs spread their weight reads over this many identical copies
     unsigned long long* dbg; // optional cycle counters of block 0 (NERFB200_TC_DEBUG), else NULL
     int dbg_mode;            // developer experiments (NERFB200_TC_DEBUG value): 2 = skip epilogue math
@@ -350,7 +382,7 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_
 
 // Inference epilogue with packed arithmetic: add.f32x2 for the bias and ONE conversion per pair with the
 // ReLU folded into it (cvt.rn.relu; rounding is monotonic and sign preserving, so it equals cvt(max(x, 0))).
-template <bool kHalf, int NG, bool kRelu, bool kSigma = false>
+template <bool kHalf, int NG, bool kRelu, bool kSigma = false, bool kBias = true>
 __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const float* s_bias, uint8_t* act, int row,
                                                      uint32_t* mask_row = nullptr, const float4* ws4 = nullptr,
                                                      float* sig_acc = nullptr) {
@@ -365,9 +397,13 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
         uint32_t o[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float4 bb = b4[i];
-            const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1])), make_float2(bb.x, bb.y));
-            const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(bb.z, bb.w));
+            float2 s0 = make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1]));
+            float2 s1 = make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3]));
+            if (kBias) {     // (the pair kernel's accumulators already contain the bias)
+                const float4 bb = b4[i];
+                s0 = __fadd2_rn(s0, make_float2(bb.x, bb.y));
+                s1 = __fadd2_rn(s1, make_float2(bb.z, bb.w));
+            }
             if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
                 const float4 w = __ldg(ws4 + 8 * g + i);
                 float acc = *sig_acc;
@@ -669,14 +705,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
     auto ring_empty = [&](int s) { return sbar + 8 * (kStages + s); };
     auto act_ready = [&](int t) { return sbar + 8 * (2 * kStages + t); };
     auto acc_full = [&](int t) { return sbar + 8 * (2 * kStages + 2 + t); };
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemBar + 8 * (2 * kStages + 4));
+    const uint32_t bias_full = sbar + 8 * (2 * kStages + 4), bias_empty = sbar + 8 * (2 * kStages + 5);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemBar + 8 * (2 * kStages + 6));
 
     if (threadIdx.x == 0) {
         // leader's ring_full: own expect_tx arrive + the peer's relay; peer's ring_full: own arrive only
         for (int s = 0; s < kStages; ++s) { mbar_init(ring_full(s), rank == 0 ? 2 : 1); mbar_init(ring_empty(s), 1); }
         // act_ready (used in the leader): one elected arrive per CTA; acc_full: one multicast commit
         for (int t = 0; t < 2; ++t) { mbar_init(act_ready(t), 2); mbar_init(acc_full(t), 1); }
+        mbar_init(bias_full, rank == 0 ? 2 : 1);     // like ring_full: own expect_tx arrive (+ the peer's relay in the leader)
+        mbar_init(bias_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 16) {
+        // "ones" A operand of the bias MMA step: core matrix 0 = 8 rows x [1, 1, 0, 0, 0, 0, 0, 0], core matrix 1 = zeros;
+        // its descriptor has SBO = 0, so all sixteen 8-row groups of the 128-row tile read these same 256 bytes
+        const uint32_t one2 = pack2<kHalf>(1.f, 1.f);
+        reinterpret_cast<uint4*>(smem + kSmemOnes)[threadIdx.x] = threadIdx.x < 8 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
     }
     cluster_sync_all();
     if (warp == kMmaWarp) {
@@ -695,10 +741,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
     if (warp == kProducerWarp) {
         // ===================== weight producer: this CTA's half of every chunk =====================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, bphase = 0;
             for (int qd = cluster_id; qd < quads; qd += num_clusters) {
                 const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;   // slots with a tile in at least one CTA
                 for (int j = 0; j < kNumJobs; ++j) {
+                    {   // this CTA's share of the layer's bias tile (single buffer, released by the last slot's bias MMA)
+                        const uint32_t bbytes = j < 9 ? 2048u : (j == 9 ? 1024u : 128u);
+                        mbar_wait(bias_empty, bphase ^ 1);
+                        mbar_expect_tx(bias_full, bbytes);
+                        bulk_g2s(sbase + kSmemBiasTile, p.wimg + p.bias_ofs + (uint32_t)(j * 2 + (int)rank) * kBiasTileBytes, bbytes, bias_full);
+                        bphase ^= 1;
+                    }
                     const int cb = c_job_begin[j];
                     const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
                     // a layer whose weights fit the ring (KC <= 4) is loaded ONCE and used by both slots
@@ -721,10 +774,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
     } else if (warp == kMmaWarp) {
         if (lane == 0 && rank == 1) {
             // ===================== peer: relay "stage landed" to the leader =====================
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, bphase = 0;
+            const uint32_t bias_full_leader = mapa(bias_full, 0);
             for (int qd = cluster_id; qd < quads; qd += num_clusters) {
                 const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;
                 for (int j = 0; j < kNumJobs; ++j) {
+                    mbar_wait(bias_full, bphase);
+                    mbar_arrive_cluster(bias_full_leader);
+                    bphase ^= 1;
                     const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
                     const int loads = ((KC <= kStages) ? 1 : nslots) * KC;
                     for (int c = 0; c < loads; ++c) {
@@ -740,7 +797,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
             // compiler needs no per-instruction election loop); one elected lane issues the tcgen05 ops
             const uint32_t ring_lo = ((sbase + kSmemRing) >> 4) & 0x3FFFu;
             constexpr uint32_t id256 = umma_idesc_pair(fmt, 256), id128 = umma_idesc_pair(fmt, 128), id16 = umma_idesc_pair(fmt, 16);
-            uint32_t stage = 0, phase = 0, act_phase_bits = 0;
+            uint32_t stage = 0, phase = 0, act_phase_bits = 0, bphase = 0;
+            // no-swizzle K-major descriptors of the bias step: A = the ones atom (LBO 128 B between its two core matrices,
+            // SBO 0: every 8-row group aliases it), B = the bias tile (SBO 128 B between 8-row groups, LBO 0: k 8..15 alias
+            // k 0..7 and meet A's zeros)
+            const uint64_t ones_desc = (uint64_t)(((sbase + kSmemOnes) >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | (1ull << 46);
+            const uint64_t biast_desc = (uint64_t)(((sbase + kSmemBiasTile) >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
             for (int qd = cluster_id; qd < quads; qd += num_clusters) {
 #pragma unroll 1
                 for (int j = 0; j < kNumJobs; ++j) {
@@ -761,6 +823,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                         const uint32_t d = tmem_base + (uint32_t)(t * 256);
                         if (shared_w) { stage = stage0; phase = phase0; }     // second slot re-walks the same stages
                         const bool first_user = !shared_w || t == 0, last_user = !shared_w || t == nslots - 1;
+                        // the layer starts from its bias: D = ones . bias_tile^T (accumulate off)
+                        if (t == 0) { NB_T0(); mbar_wait_cluster(bias_full, bphase); NB_T1(1); tc_fence_after(); bphase ^= 1; }
+                        if (elect_one_sync()) {
+                            umma_f16_pair(d, ones_desc, biast_desc, idesc, 0u);
+                            if (t == nslots - 1) umma_commit_pair(bias_empty);
+                        }
+                        __syncwarp();
 #pragma unroll 1
                         for (int kc = 0; kc < KC; ++kc) {
                             if (first_user) { NB_T0(); mbar_wait_cluster(ring_full(stage), phase); NB_T1(1); tc_fence_after(); }
@@ -768,7 +837,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                             const uint32_t a_lo = is_enc ? enc_lo : act_lo + (uint32_t)(kc * 1024);
                             const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
                             if (elect_one_sync()) {
-                                umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
+                                umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, 1u);
                                 umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
                                 if (!(is_enc && enc_short)) {
                                     umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
@@ -789,7 +858,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
         const int t = warp >> 2, q = warp & 3, row = q * 32 + lane;
         uint8_t* act = smem + kSmemAct + t * kActBytes;
         uint8_t* enc = smem + kSmemEnc + t * kEncBytes;
-        float* s_bias = reinterpret_cast<float*>(smem + kSmemBias + t * 1024);
+        const float* s_bias = nullptr;      // the accumulators already contain the bias (first MMA of every layer)
         const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
         const uint32_t act_ready_leader = mapa(act_ready(t), 0);
         uint32_t acc_phase = 0;
@@ -821,13 +890,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     if (issued) bulk_commit_group();
                 }
                 pendA_bytes = 0; pendE_bytes = 0;
-                {
-                    const int N = j < 9 ? 256 : (j == 9 ? 128 : 16);
-                    const float* b = p.heads + HeadOffsets::bias(j);
-                    if (row < N) s_bias[row] = __ldg(b + row);
-                    if (row + 128 < N) s_bias[row + 128] = __ldg(b + row + 128);
-                }
-                named_bar_sync(1 + t, kTileRows);
                 { NB_T0(); mbar_wait(acc_full(t), acc_phase); NB_T1(0); }
                 acc_phase ^= 1;
                 tc_fence_after();
@@ -840,19 +902,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     if (kTrain) {
                         uint32_t* mrow = nullptr;
                         if (tstash && j != 8) mrow = reinterpret_cast<uint32_t*>(tstash + kStashMaskOfs) + ((j == 9 ? 8 : j) * 128 + row) * 8;
-                        if (j == 7) epilogue_cols_packed<kHalf, 8, true, true>(tmem_row, s_bias, act, row, mrow, ws4, &sig_acc);
-                        else if (j == 8) epilogue_cols_packed<kHalf, 8, false>(tmem_row, s_bias, act, row);
-                        else if (j == 9) epilogue_cols_packed<kHalf, 4, true>(tmem_row, s_bias, act, row, mrow);
-                        else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row, mrow);
+                        if (j == 7) epilogue_cols_packed<kHalf, 8, true, true, false>(tmem_row, s_bias, act, row, mrow, ws4, &sig_acc);
+                        else if (j == 8) epilogue_cols_packed<kHalf, 8, false, false, false>(tmem_row, s_bias, act, row);
+                        else if (j == 9) epilogue_cols_packed<kHalf, 4, true, false, false>(tmem_row, s_bias, act, row, mrow);
+                        else epilogue_cols_packed<kHalf, 8, true, false, false>(tmem_row, s_bias, act, row, mrow);
                         if (tstash) {
                             pendA_dst = tstash + (j < 8 ? stash_chunk_Y(j) : j == 8 ? kStashChunkBott : kStashChunkY9) * 16384;
                             pendA_bytes = j == 9 ? 2 * 16384 : 4 * 16384;
                         }
                     } else {
-                        if (j == 7) epilogue_cols_packed<kHalf, 8, true, true>(tmem_row, s_bias, act, row, nullptr, ws4, &sig_acc);
-                        else if (j == 8) epilogue_cols_packed<kHalf, 8, false>(tmem_row, s_bias, act, row);
-                        else if (j == 9) epilogue_cols_packed<kHalf, 4, true>(tmem_row, s_bias, act, row);
-                        else epilogue_cols_packed<kHalf, 8, true>(tmem_row, s_bias, act, row);
+                        if (j == 7) epilogue_cols_packed<kHalf, 8, true, true, false>(tmem_row, s_bias, act, row, nullptr, ws4, &sig_acc);
+                        else if (j == 8) epilogue_cols_packed<kHalf, 8, false, false, false>(tmem_row, s_bias, act, row);
+                        else if (j == 9) epilogue_cols_packed<kHalf, 4, true, false, false>(tmem_row, s_bias, act, row);
+                        else epilogue_cols_packed<kHalf, 8, true, false, false>(tmem_row, s_bias, act, row);
                     }
                     if (j == 5) {
                         long long _td = dbg_on ? clock64() : 0;
@@ -883,7 +945,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     tmem_ld_wait(r);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float x = __uint_as_float(r[c]) + s_bias[c];
+                        const float x = __uint_as_float(r[c]);
                         const float y = 1.f / (1.f + expf(-x));
                         if (cur.valid) p.rgb[3 * cur.grow + c] = y;
                         if (kTrain && tstash) reinterpret_cast<float*>(tstash + kStashOutOfs)[3 * row + c] = cur.valid ? y : 0.f;
@@ -1275,7 +1337,7 @@ void tc_destroy(nerfb200_ctx* ctx) {
 
 int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st) {
     const ChunkTable& t = chunk_table();
-    int64_t units = t.bytes / 16;
+    int64_t units = t.bias_ofs / 16;
     for (int m = 0; m < 2; ++m) {
         const float* P = flat_params + (int64_t)m * kParamsPerModel;
         pack_weights_kernel<__nv_bfloat16><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m], t.n);
@@ -1284,6 +1346,8 @@ int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st
             for (int r = 1; r < ctx->replicas; ++r)
                 NB_CUDA(cudaMemcpyAsync((uint8_t*)ctx->packed[pz][m] + (size_t)r * t.bytes, ctx->packed[pz][m], t.bytes,
                                         cudaMemcpyDeviceToDevice, st));
+        pack_bias_tiles_kernel<__nv_bfloat16><<<(kNumJobs * 256 + 255) / 256, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m] + t.bias_ofs);
+        pack_bias_tiles_kernel<__half><<<(kNumJobs * 256 + 255) / 256, 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m] + t.bias_ofs);
         pack_heads_kernel<<<(HeadOffsets::total + 255) / 256, 256, 0, st>>>(P, ctx->head_params[m]);
     }
     NB_LAUNCH_CHECK();
@@ -1303,6 +1367,7 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
     TcParams p;
     p.wimg = (const uint8_t*)ctx->packed[half ? 1 : 0][which];
     p.wimg_stride = chunk_table().bytes;
+    p.bias_ofs = chunk_table().bias_ofs;
     p.replicas = ctx->replicas;
     p.heads = ctx->head_params[which];
     p.ro = ro; p.rd = rd; p.t = t; p.rgb = rgb; p.sigma = sigma; p.R = R; p.S = S;
