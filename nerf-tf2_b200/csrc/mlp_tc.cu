@@ -825,30 +825,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                         const bool first_user = !shared_w || t == 0, last_user = !shared_w || t == nslots - 1;
                         // the layer starts from its bias: D = ones . bias_tile^T (accumulate off)
                         if (t == 0) { NB_T0(); mbar_wait_cluster(bias_full, bphase); NB_T1(1); tc_fence_after(); bphase ^= 1; }
+                        // ONE election per (layer, slot): the elected lane walks the K chunks alone (waits, MMAs, commits);
+                        // an election + reconvergence per chunk costs ~200 cycles of issue time (tools/umma_probe.cu)
                         if (elect_one_sync()) {
                             umma_f16_pair(d, ones_desc, biast_desc, idesc, 0u);
                             if (t == nslots - 1) umma_commit_pair(bias_empty);
-                        }
-                        __syncwarp();
+                            uint32_t st = stage, ph = phase;
 #pragma unroll 1
-                        for (int kc = 0; kc < KC; ++kc) {
-                            if (first_user) { NB_T0(); mbar_wait_cluster(ring_full(stage), phase); NB_T1(1); tc_fence_after(); }
-                            const bool is_enc = kc == enc_kc;
-                            const uint32_t a_lo = is_enc ? enc_lo : act_lo + (uint32_t)(kc * 1024);
-                            const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
-                            if (elect_one_sync()) {
+                            for (int kc = 0; kc < KC; ++kc) {
+                                if (first_user) { NB_T0(); mbar_wait_cluster(ring_full(st), ph); NB_T1(1); tc_fence_after(); }
+                                const bool is_enc = kc == enc_kc;
+                                const uint32_t a_lo = is_enc ? enc_lo : act_lo + (uint32_t)(kc * 1024);
+                                const uint32_t b_lo = ring_lo + st * (kStageBytes >> 4);
                                 umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, 1u);
                                 umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
                                 if (!(is_enc && enc_short)) {
                                     umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
                                     umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
                                 }
-                                if (last_user) umma_commit_pair(ring_empty(stage));
+                                if (last_user) umma_commit_pair(ring_empty(st));
                                 if (kc == KC - 1) umma_commit_pair(acc_full(t));
+                                if (++st == kStages) { st = 0; ph ^= 1; }
                             }
-                            __syncwarp();
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
+                        __syncwarp();
+                        // every lane advances the ring position by KC stages
+                        phase ^= ((stage + (uint32_t)KC) / kStages) & 1u;
+                        stage = (stage + (uint32_t)KC) % kStages;
                     }
                 }
             }
