@@ -439,22 +439,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBThreads, 1) bwd_da
                         const uint32_t d = tmem_base + (uint32_t)(t * 256);
                         stage = stage0; phase = phase0;
                         const bool first_user = t == 0, last_user = t == nslots - 1;
+                        // one election per (job, slot): the elected lane walks the K chunks alone (see the forward kernel)
+                        if (elect_one_sync()) {
+                            uint32_t st = stage, ph = phase;
 #pragma unroll 1
-                        for (int kc = 0; kc < KC; ++kc) {
-                            if (first_user) { mbar_wait_cluster(ring_full(stage), phase); tc_fence_after(); }
-                            const uint32_t a_lo = act_lo + (uint32_t)(kc * 1024);
-                            const uint32_t b_lo = ring_lo + stage * (kChunkBytes >> 4);
-                            if (elect_one_sync()) {
+                            for (int kc = 0; kc < KC; ++kc) {
+                                if (first_user) { mbar_wait_cluster(ring_full(st), ph); tc_fence_after(); }
+                                const uint32_t a_lo = act_lo + (uint32_t)(kc * 1024);
+                                const uint32_t b_lo = ring_lo + st * (kChunkBytes >> 4);
                                 umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
                                 umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
                                 umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
                                 umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
-                                if (last_user) umma_commit_pair(ring_empty(stage));
+                                if (last_user) umma_commit_pair(ring_empty(st));
                                 if (kc == KC - 1) umma_commit_pair(sbar + 8 * (2 * kBStages + 2 + t));
+                                if (++st == kBStages) { st = 0; ph ^= 1; }
                             }
-                            __syncwarp();
-                            if (++stage == kBStages) { stage = 0; phase ^= 1; }
                         }
+                        __syncwarp();
+                        phase ^= ((stage + (uint32_t)KC) / kBStages) & 1u;
+                        stage = (stage + (uint32_t)KC) % kBStages;
                     }
                 }
             }
