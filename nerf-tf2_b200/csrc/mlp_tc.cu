@@ -388,6 +388,7 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
                                                      float* sig_acc = nullptr) {
     uint32_t r[2][32];
     tmem_ld32(tmem_row, r[0]);
+    float sg[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         uint32_t (&rr)[32] = r[g & 1];
@@ -404,14 +405,13 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
                 s0 = __fadd2_rn(s0, make_float2(bb.x, bb.y));
                 s1 = __fadd2_rn(s1, make_float2(bb.z, bb.w));
             }
-            if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
+            if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375); four independent partial sums:
+                            // one 256-long dependent FMA chain was ~5 k cycles on the slot's critical path
                 const float4 w = __ldg(ws4 + 8 * g + i);
-                float acc = *sig_acc;
-                acc = fmaf(fmaxf(s0.x, 0.f), w.x, acc);
-                acc = fmaf(fmaxf(s0.y, 0.f), w.y, acc);
-                acc = fmaf(fmaxf(s1.x, 0.f), w.z, acc);
-                acc = fmaf(fmaxf(s1.y, 0.f), w.w, acc);
-                *sig_acc = acc;
+                sg[0] = fmaf(fmaxf(s0.x, 0.f), w.x, sg[0]);
+                sg[1] = fmaf(fmaxf(s0.y, 0.f), w.y, sg[1]);
+                sg[2] = fmaf(fmaxf(s1.x, 0.f), w.z, sg[2]);
+                sg[3] = fmaf(fmaxf(s1.y, 0.f), w.w, sg[3]);
             }
             if (kRelu) { o[2 * i] = pack2_relu<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2_relu<kHalf>(s1.x, s1.y); }
             else { o[2 * i] = pack2<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2<kHalf>(s1.x, s1.y); }
@@ -428,6 +428,7 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
         for (int u = 0; u < 4; ++u)
             *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
     }
+    if (kSigma) *sig_acc += (sg[0] + sg[1]) + (sg[2] + sg[3]);
 }
 
 #define NB_T0() long long _t0 = dbg_on ? clock64() : 0
@@ -815,7 +816,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     const uint32_t stage0 = stage, phase0 = phase;
 #pragma unroll 1
                     for (int t = 0; t < nslots; ++t) {
-                        { NB_T0(); mbar_wait_cluster(act_ready(t), (act_phase_bits >> t) & 1u); NB_T1(0); }
+                        { NB_T0(); mbar_wait_cluster(act_ready(t), (act_phase_bits >> t) & 1u); NB_T1(0);
+                          if (dbg_on && blockIdx.x == 0 && lane == 0) p.dbg[64 + j * 2 + t] += (unsigned long long)(clock64() - _t0); }
                         act_phase_bits ^= 1u << t;
                         tc_fence_after();
                         const uint32_t act_lo = ((sbase + kSmemAct + t * kActBytes) >> 4) & 0x3FFFu;
@@ -1382,8 +1384,8 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
     p.dbg = nullptr;
     p.dbg_mode = debug ? atoi(getenv("NERFB200_TC_DEBUG")) : 0;
     if (debug) {
-        NB_CUDA(cudaMalloc((void**)&p.dbg, 64 * sizeof(unsigned long long)));
-        NB_CUDA(cudaMemsetAsync(p.dbg, 0, 64 * sizeof(unsigned long long), st));
+        NB_CUDA(cudaMalloc((void**)&p.dbg, 128 * sizeof(unsigned long long)));
+        NB_CUDA(cudaMemsetAsync(p.dbg, 0, 128 * sizeof(unsigned long long), st));
     }
     static const bool use_pair = getenv("NERFB200_TC_PAIR") ? atoi(getenv("NERFB200_TC_PAIR")) != 0 : true;
     static const bool use_v3 = getenv("NERFB200_TC_V3") ? atoi(getenv("NERFB200_TC_V3")) != 0 : false;
@@ -1411,7 +1413,7 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
     }
     NB_LAUNCH_CHECK();
     if (debug) {
-        unsigned long long h[64];
+        unsigned long long h[128];
         NB_CUDA(cudaMemcpyAsync(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
         NB_CUDA(cudaStreamSynchronize(st));
         cudaFree(p.dbg);
@@ -1420,6 +1422,9 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
         for (int r = 0; r < 8; ++r)
             fprintf(stderr, "  cta%d %-8s wait0=%llu wait1/epi=%llu encdir=%llu prep=%llu total=%llu\n", r / 4, names[r % 4], h[r * 8],
                     h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
+        fprintf(stderr, "  issuer wait for operands by job (slot0/slot1, cycles):");
+        for (int j = 0; j < kNumJobs; ++j) fprintf(stderr, " j%d %llu/%llu", j, h[64 + 2 * j], h[64 + 2 * j + 1]);
+        fprintf(stderr, "\n");
     }
     return 0;
 }
