@@ -816,8 +816,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                     const uint32_t stage0 = stage, phase0 = phase;
 #pragma unroll 1
                     for (int t = 0; t < nslots; ++t) {
-                        { NB_T0(); mbar_wait_cluster(act_ready(t), (act_phase_bits >> t) & 1u); NB_T1(0);
-                          if (dbg_on && blockIdx.x == 0 && lane == 0) p.dbg[64 + j * 2 + t] += (unsigned long long)(clock64() - _t0); }
+                        { NB_T0(); mbar_wait_cluster(act_ready(t), (act_phase_bits >> t) & 1u); NB_T1(0); }
                         act_phase_bits ^= 1u << t;
                         tc_fence_after();
                         const uint32_t act_lo = ((sbase + kSmemAct + t * kActBytes) >> 4) & 0x3FFFu;
@@ -1422,9 +1421,6 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
         for (int r = 0; r < 8; ++r)
             fprintf(stderr, "  cta%d %-8s wait0=%llu wait1/epi=%llu encdir=%llu prep=%llu total=%llu\n", r / 4, names[r % 4], h[r * 8],
                     h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
-        fprintf(stderr, "  issuer wait for operands by job (slot0/slot1, cycles):");
-        for (int j = 0; j < kNumJobs; ++j) fprintf(stderr, " j%d %llu/%llu", j, h[64 + 2 * j], h[64 + 2 * j + 1]);
-        fprintf(stderr, "\n");
     }
     return 0;
 }
