@@ -692,12 +692,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
 // Roles per CTA are as in the single-CTA kernel; only the leader's warp 9 issues MMAs, the peer's warp 9
 // relays "my half of the weight stage has landed" to the leader's ring barrier. tcgen05.commit multicasts
 // completion to both CTAs' barriers.
-template <bool kHalf, bool kTrain>
+template <bool kHalf, bool kTrain, bool kDbg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_forward_pair_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const bool dbg_on = p.dbg != nullptr && blockIdx.x < 2;
+    // cycle counters exist only in the kDbg instantiation: even predicated-off code in the issuer loop costs throughput
+    const bool dbg_on = kDbg && p.dbg != nullptr && blockIdx.x < 2;
     unsigned long long dbg_acc0 = 0, dbg_acc1 = 0, dbg_acc2 = 0, dbg_acc3 = 0;
     const long long t_kernel0 = clock64();
     const uint32_t sbase = smem_u32(smem);
@@ -1323,10 +1324,14 @@ int tc_create(nerfb200_ctx* ctx) {
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemTotal));
     NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemTotal));
     return tc_train_create(ctx);
@@ -1396,13 +1401,17 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
     } else if (use_pair) {
         int quads = (p.num_tiles + 3) / 4;
         int clusters = quads < ctx->num_sms / 2 ? quads : ctx->num_sms / 2;
+#define NB_LAUNCH_PAIR(H, T)                                                                                   \
+    do {                                                                                                       \
+        if (debug) mlp_tc_forward_pair_kernel<H, T, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);      \
+        else mlp_tc_forward_pair_kernel<H, T, false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);           \
+    } while (0)
         if (stash) {
-            if (half) mlp_tc_forward_pair_kernel<true, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
-            else mlp_tc_forward_pair_kernel<false, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+            if (half) NB_LAUNCH_PAIR(true, true); else NB_LAUNCH_PAIR(false, true);
         } else {
-            if (half) mlp_tc_forward_pair_kernel<true, false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
-            else mlp_tc_forward_pair_kernel<false, false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+            if (half) NB_LAUNCH_PAIR(true, false); else NB_LAUNCH_PAIR(false, false);
         }
+#undef NB_LAUNCH_PAIR
     } else if (stash) {
         if (half) mlp_tc_forward_kernel<true, true><<<grid, kThreads, kSmemTotal, st>>>(p);
         else mlp_tc_forward_kernel<false, true><<<grid, kThreads, kSmemTotal, st>>>(p);
