@@ -161,3 +161,24 @@ def test_full_size_800x800_properties():
     nerf.render_chunk = 50000
     out2 = nb.render.render_view(nerf, H, W, sc.poses[2], sc.bounds, sc.K, depth_maps=False)
     assert torch.equal(out["img_u8"], out2["img_u8"])
+
+
+def test_bench_line_contract():
+    """One short bench run on the GPU: ONE JSON line with the contract's keys (value/e2e/roofline/gpu_launches/clocks)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu", "--no-train"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["unit"] == "rays/s" and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "bf16" and d["data"] == "synthetic"
+    assert d["value"] > 1e5 and d["gpu_launches"] > 0 and d["warmup"] >= 3
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and 0 < r["frac"] < 1.5 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    e = d["e2e"]
+    assert e["value"] > 1e5 and e["h2d_bytes_per_step"] == 640000 * 8 * 4 and e["d2h_bytes_per_step"] == 640000 * 10 * 4
+    assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"] and "workload" in d["config"]
