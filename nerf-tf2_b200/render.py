@@ -21,10 +21,13 @@ from ._lib import check, load, ptr, stream_ptr
 
 
 def render_view(nerf, H, W, c2w, bounds, intrinsic, gt_u8=None, scale_factor=None, depth_maps=True,
-                ray0=0, n_rays=None):
-    """Renders one view (or the ray range [ray0, ray0+n_rays) of it). Returns a dict of DEVICE tensors:
-    img_u8 [n,3], acc_map [n], depth_type_1 [n], depth_type_2 [n] (full views only) and `psnr` (float,
-    eval.py definition) when `gt_u8` ([H,W,3] or [n,3] uint8) is given."""
+                ray0=0, n_rays=None, c2w_W2=None):
+    """Renders one view (or the ray range [ray0, ray0+n_rays) of it). `c2w`/`bounds` are the W3 (scene-scaled) pose
+    and bounds the rays are marched with. Returns a dict of DEVICE tensors: img_u8 [n,3], acc_map [n],
+    depth_type_1 [n], depth_type_2 [n] (full views only) and `psnr` (float, eval.py definition) when `gt_u8`
+    ([H,W,3] or [n,3] uint8) is given. The depth maps are in W2 units like main/render.py:103-112: type_1 is
+    depth / scale_factor, type_2 the camera-space z of `o + d * depth / scale_factor` for the UNSCALED camera->W2
+    pose -- `c2w_W2`, or `c2w` with the scene scale undone when it is not given."""
     dev = nerf.device
     n = H * W - ray0 if n_rays is None else n_rays
     ro, rd = ray_utils.get_rays(H, W, intrinsic, c2w, ray0, n, device=dev)
@@ -50,8 +53,12 @@ def render_view(nerf, H, W, c2w, bounds, intrinsic, gt_u8=None, scale_factor=Non
     if depth_maps and scale_factor is not None:
         out["depth_type_1"] = fine["pred_depth"] * (1 / scale_factor)
         if ray0 == 0 and n == H * W:
+            if c2w_W2 is None:      # reconfigure_scene_scale applied diag(s,s,s,1) only when s < 1 (pose_utils.py:427-463)
+                c2w_W2 = np.asarray(c2w, dtype=np.float64)
+                if scale_factor < 1:
+                    c2w_W2 = np.diag([1 / scale_factor] * 3 + [1.0]) @ c2w_W2
             out["depth_type_2"] = ray_utils.create_depth_map(fine["pred_depth"], H, W, scale_factor, "type_2",
-                                                             intrinsic, c2w).reshape(-1)
+                                                             intrinsic, c2w_W2).reshape(-1)
     return out
 
 
@@ -74,3 +81,49 @@ def evaluate_views(nerf, H, W, poses, bounds, intrinsic, gts_u8, scale_factor=No
         tdist.all_reduce(local, group=process_group)
     vals = local.cpu().numpy()
     return {"psnr_vals": vals, "mean_psnr": float(vals.mean()), "last_view_psnr": float(vals[-1])}
+
+
+def render_spherical_path(nerf, render_params, adj_scale_factor, save_dir=None):
+    """The loop of main/render.py:51-117: `num_cameras` poses on a sphere (create_spherical_path, in W2), intrinsics from
+    the COLMAP camera model, bounds = 0.25/0.75 of the diameter unless given, every view scaled to W3 with
+    `adj_scale_factor` (what create_dataset_for_render does with reconfig_poses=False) and ray-marched on the device.
+    Returns a list of dicts with HOST arrays `img_u8 [H,W,3]`, `depth_type_1 [H,W]`, `depth_type_2 [H,W]`,
+    `acc_map [H,W]`; with `save_dir`, also writes rgb/*.png and depth_type_1|depth_type_2|acc_map/*.npy under the
+    script's names (render_00000.png ...)."""
+    from . import pose_utils
+    from .datasets import CustomDataset
+    poses = pose_utils.create_spherical_path(radius=render_params.radius, num_cameras=render_params.num_cameras,
+                                             inclination=render_params.inclination,
+                                             manual_rotation=render_params.manual_rotation)
+    K = CustomDataset.camera_model_params_to_intrinsics(render_params.camera_model_name, render_params.camera_model_params)
+    if render_params.bounds is None:
+        diameter = 2 * render_params.radius
+        bounds = np.array([0.25 * diameter, 0.75 * diameter], dtype=np.float64)
+    else:
+        bounds = np.array(render_params.bounds, dtype=np.float64)
+    H, W = render_params.img_size
+    s = float(adj_scale_factor)
+    zfill = int(np.log10(render_params.num_cameras) + 5)
+    dirs = {}
+    if save_dir is not None:
+        import os
+        for sub in ("rgb", "depth_type_1", "depth_type_2", "acc_map"):
+            dirs[sub] = os.path.join(save_dir, sub)
+            os.makedirs(dirs[sub], exist_ok=True)
+    frames = []
+    for i in range(render_params.num_cameras):
+        pose3, bounds3 = pose_utils.reconfigure_scene_scale(poses[i], bounds, s)
+        r = render_view(nerf, H, W, pose3, bounds3, K, scale_factor=s, c2w_W2=poses[i])
+        out = {"img_u8": r["img_u8"].reshape(H, W, 3).cpu().numpy(),
+               "depth_type_1": r["depth_type_1"].reshape(H, W).cpu().numpy(),
+               "depth_type_2": r["depth_type_2"].reshape(H, W).cpu().numpy(),
+               "acc_map": r["acc_map"].reshape(H, W).cpu().numpy()}
+        frames.append(out)
+        if save_dir is not None:
+            import os
+            from PIL import Image
+            name = f"render_{str(i).zfill(zfill)}"
+            Image.fromarray(out["img_u8"]).save(os.path.join(dirs["rgb"], f"{name}.png"))
+            for k in ("depth_type_1", "depth_type_2", "acc_map"):
+                np.save(os.path.join(dirs[k], f"{name}.npy"), out[k])
+    return frames

@@ -62,9 +62,15 @@ def test_render_view_postprocessing_matches_reference_scripts():
     ref_psnr = rm.psnr_metric_numpy(gt.reshape(-1, 3).astype(F32) / 255.0, clipped.astype(F32) / 255.0)
     assert abs(out["psnr"] - float(ref_psnr)) <= 1e-4
     depth = host(out["pred_depth"])
+    # main/render.py:103-112: both depth maps are taken with the camera->W2 pose (the spherical-path pose BEFORE the
+    # scene scale); render_view undoes the scale of the W3 pose it was given
+    c2w_W2 = rm.create_spherical_path(4.0, 40.0, 8)[3]
     for mt in ("type_1", "type_2"):
-        ref = rm.create_depth_map(depth, H, W, v["adj_scale_factor"], mt, v["K"], v["c2w"]).reshape(-1)
-        assert np.allclose(host(out[f"depth_{mt}"]), ref, rtol=2e-6, atol=1e-6)
+        ref = rm.create_depth_map(depth, H, W, v["adj_scale_factor"], mt, v["K"], c2w_W2).reshape(-1)
+        assert np.allclose(host(out[f"depth_{mt}"]), ref, rtol=2e-6, atol=2e-6)
+    # type_2 is a camera-space z: positive, and never larger than the type_1 distance along the ray
+    z, dist = host(out["depth_type_2"]), host(out["depth_type_1"])
+    assert np.all(z > 0) and np.all(z <= dist * (1 + 1e-5))
     # a ray sub-range renders the same pixels as the full view (fixed sampling: perturb off would still
     # draw random fine uniforms, keyed by GLOBAL ray id, so ranges agree exactly)
     part = nb.render.render_view(nerf, H, W, v["c2w"], v["bounds"], v["K"], ray0=100, n_rays=160)
@@ -182,3 +188,25 @@ def test_bench_line_contract():
     e = d["e2e"]
     assert e["value"] > 1e5 and e["h2d_bytes_per_step"] == 640000 * 8 * 4 and e["d2h_bytes_per_step"] == 640000 * 10 * 4
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"] and "workload" in d["config"]
+
+
+def test_render_spherical_path_script_loop(tmp_path):
+    """main/render.py:51-117 as a function: poses on a sphere, W3 scaling, uint8 frames + both depth maps + acc map,
+    files named like the script's."""
+    params = nb.make_params({"system": {"white_bg": True}, "render": {"radius": 4.0, "inclination": 40.0, "num_cameras": 3,
+                                                                      "img_size": [10, 12], "camera_model_name": "SIMPLE_PINHOLE",
+                                                                      "camera_model_params": [16.0, 6.0, 5.0], "bounds": None}},
+                            perturb=False)
+    nerf = nb.setup_model(params, precision="bf16", seed=3)
+    frames = nb.render.render_spherical_path(nerf, params.render, adj_scale_factor=0.2125, save_dir=str(tmp_path))
+    assert len(frames) == 3 and frames[0]["img_u8"].shape == (10, 12, 3) and frames[0]["img_u8"].dtype == np.uint8
+    assert frames[1]["depth_type_1"].shape == (10, 12) and frames[1]["depth_type_2"].shape == (10, 12)
+    assert sorted(os.listdir(tmp_path / "rgb")) == ["render_00000.png", "render_00001.png", "render_00002.png"]
+    assert np.array_equal(np.load(tmp_path / "acc_map" / "render_00002.npy"), frames[2]["acc_map"])
+    # the same view through render_view with explicit W3 pose / bounds (0.25 and 0.75 of the diameter, scaled)
+    from nerf_tf2_b200 import pose_utils as pu
+    pose2 = pu.create_spherical_path(4.0, 40.0, 3, None)[1]
+    pose3, b3 = pu.reconfigure_scene_scale(pose2, np.array([2.0, 6.0]), 0.2125)
+    K = nb.CustomDataset.camera_model_params_to_intrinsics("SIMPLE_PINHOLE", [16.0, 6.0, 5.0])
+    r = nb.render.render_view(nerf, 10, 12, pose3, b3, K, scale_factor=0.2125, c2w_W2=pose2)
+    assert np.array_equal(host(r["img_u8"]).reshape(10, 12, 3), frames[1]["img_u8"])
