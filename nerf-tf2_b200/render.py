@@ -127,3 +127,32 @@ def render_spherical_path(nerf, render_params, adj_scale_factor, save_dir=None):
             for k in ("depth_type_1", "depth_type_2", "acc_map"):
                 np.save(os.path.join(dirs[k], f"{name}.npy"), out[k])
     return frames
+
+
+def evaluate_split(nerf, dataset_obj, data, save_dir=None):
+    """The loop of main/eval.py:26-67 over one split's SceneLevelData (`data`, poses still in W1 as the loaders return
+    them): each pose goes W1 -> W2 -> W3 through the saved reconfig.npz (what create_dataset_for_render does with
+    reconfig_poses=True), the view is ray-marched and scored against its image with the script's PSNR. Returns
+    {"psnr_vals", "mean_psnr", "last_view_psnr"} (the script logs np.mean of the LAST psnr only) and,
+    with `save_dir`, writes eval_00000.png ... like the script."""
+    from . import pose_utils
+    T, adj = dataset_obj.load_reconfig_params()
+    H, W = data.imgs[0].shape[:2]
+    zfill = int(np.log10(len(data.imgs)) + 5)
+    if save_dir is not None:
+        import os
+        os.makedirs(save_dir, exist_ok=True)
+    vals = []
+    for i in range(len(data.imgs)):
+        K = np.asarray(data.intrinsics[i], dtype=np.float64)
+        dataset_obj._validate_intrinsic_matrix(K=K)
+        pose2 = pose_utils.reconfigure_poses(np.asarray(data.poses[i], dtype=np.float64), T)
+        pose3, bounds3 = pose_utils.reconfigure_scene_scale(pose2, np.asarray(data.bounds[i], dtype=np.float64), adj)
+        r = render_view(nerf, H, W, pose3, bounds3, K, gt_u8=data.imgs[i], depth_maps=False)
+        vals.append(r["psnr"])
+        if save_dir is not None:
+            import os
+            from PIL import Image
+            Image.fromarray(r["img_u8"].reshape(H, W, 3).cpu().numpy()).save(os.path.join(save_dir, f"eval_{str(i).zfill(zfill)}.png"))
+    vals = np.asarray(vals, dtype=np.float64)
+    return {"psnr_vals": vals, "mean_psnr": float(vals.mean()), "last_view_psnr": float(vals[-1])}

@@ -260,3 +260,25 @@ def test_dataset_objects_feed_the_model(scenes, mode):
     np.testing.assert_allclose(first[0][0].cpu().numpy(), want_o, rtol=1e-6)
     np.testing.assert_allclose(float(first[3][0]), 6.0 * float(adj), rtol=1e-6)
     assert sum(b[0][0].shape[0] for b in rds) == H * W
+
+
+@pytest.mark.gpu
+def test_evaluate_split_is_the_eval_script_loop(scenes, tmp_path):
+    """main/eval.py over the tiny blender scene: W1 poses through reconfig.npz, per-image PSNR, eval_*.png files."""
+    save_dir = os.path.join(scenes["root"], "meta_eval")
+    params = _params("BlenderDataset", scenes["blender"], save_dir)
+    data_splits, num_imgs, obj = nb.get_data_and_metadata_for_splits(params, return_dataset_obj=True)
+    obj.validate_and_reconfigure_data(data_splits)                    # writes reconfig.npz, as a training run would have
+    nerf = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, N_coarse=32, N_fine=32), precision="bf16", seed=1)
+    res = nb.render.evaluate_split(nerf, obj, data_splits["test"], save_dir=str(tmp_path))
+    assert res["psnr_vals"].shape == (num_imgs["test"],) and np.all(np.isfinite(res["psnr_vals"]))
+    assert sorted(os.listdir(tmp_path)) == [f"eval_{i:05d}.png" for i in range(num_imgs["test"])]
+    # the first view by hand: same pose chain, same image
+    T, adj = obj.load_reconfig_params()
+    d = data_splits["test"]
+    pose3, b3 = pu.reconfigure_scene_scale(pu.reconfigure_poses(d.poses[0].astype(np.float64), T), d.bounds[0].astype(np.float64), adj)
+    H, W = d.imgs[0].shape[:2]
+    r = nb.render.render_view(nerf, H, W, pose3, b3, d.intrinsics[0].astype(np.float64), gt_u8=d.imgs[0], depth_maps=False)
+    assert abs(r["psnr"] - res["psnr_vals"][0]) < 1e-9
+    from PIL import Image
+    assert np.array_equal(np.array(Image.open(tmp_path / "eval_00000.png")), r["img_u8"].reshape(H, W, 3).cpu().numpy())
