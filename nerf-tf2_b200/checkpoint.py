@@ -84,8 +84,17 @@ def save_optimizer(path, nerf):
 class CustomSaver:
     """ops.CustomSaver: saves sub-model weights, optimiser state and logs after each validation run."""
 
-    def __init__(self, save_dir, save_best_only=False, save_optimizer_state=True, weights_format="npz"):
+    def __init__(self, save_dir=None, save_best_only=False, save_optimizer_state=True, weights_format="npz", params=None):
+        """`CustomSaver(params=params, save_best_only=False)` as in the reference (core/ops.py:98-108: the directory and
+        the optimizer switch come from params.model.save), or the directory given directly."""
+        if params is None and hasattr(save_dir, "model"):        # the reference passes params first
+            params, save_dir = save_dir, None
+        if params is not None:
+            save_dir = params.model.save.save_dir if save_dir is None else save_dir
+            save_optimizer_state = params.model.save.save_optimizer_state
+        assert save_dir is not None, "CustomSaver needs params or a save directory"
         assert weights_format in ("npz", "h5")
+        self.params = params
         self.weights_format = weights_format
         self.root = save_dir
         self.best_score = -1

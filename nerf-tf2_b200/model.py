@@ -252,12 +252,14 @@ class NeRF:
             var.assign(w[var.name])
         self._dirty = True
 
-    def set_everything(self, load_dir=None, load_tag=None, skip_optimizer=False):
-        """NeRF.set_everything (core/model.py:239-287); paths default to params.model.load.*"""
+    def set_everything(self, load_dir=None, load_tag=None, skip_optimizer=None):
+        """NeRF.set_everything (core/model.py:239-287); directory, tag and skip_optimizer default to params.model.load.*"""
         from . import checkpoint
         load = getattr(getattr(self.params, "model", None), "load", None)
         load_dir = load_dir if load_dir is not None else load.load_dir
         load_tag = load_tag if load_tag is not None else load.load_tag
+        if skip_optimizer is None:
+            skip_optimizer = bool(getattr(load, "skip_optimizer", False)) if load is not None else False
         checkpoint.set_everything(self, load_dir, load_tag, skip_optimizer)
 
     def _sync_packed(self):
@@ -636,8 +638,20 @@ def get_coarse_or_fine_model(model_name, num_units=256, params=None, **kw):
 
 
 def setup_model(params, **kw):
-    """setup_model (core/model.py:396-432): Adam(ExponentialDecay(5e-4, 500000, 0.1)) + PSNRMetric."""
+    """setup_model (core/model.py:396-432): Adam(ExponentialDecay(5e-4, 500000, 0.1)) + PSNRMetric; weights and
+    optimiser state are restored from params.model.load.* when `set_weights` is on."""
     nerf = NeRF(params=params, **kw)
     nerf.compile(optimizer="adam", metrics=[ops.PSNRMetric()],
                  run_eagerly=getattr(params.system, "run_eagerly", False))
+    load = getattr(getattr(params, "model", None), "load", None)
+    if load is not None and getattr(load, "set_weights", False):
+        nerf.set_everything()
     return nerf
+
+
+def setup_model_and_callbacks(params, num_imgs=None, img_HW=None, **kw):
+    """setup_model_and_callbacks (core/model.py:434-483): the CustomSaver callback + the model. The reference's
+    TensorBoard and LogValImages callbacks are logging only and not provided (out of scope)."""
+    from .checkpoint import CustomSaver
+    callbacks = [CustomSaver(params=params, save_best_only=False)]
+    return setup_model(params, **kw), callbacks

@@ -282,3 +282,31 @@ def test_evaluate_split_is_the_eval_script_loop(scenes, tmp_path):
     assert abs(r["psnr"] - res["psnr_vals"][0]) < 1e-9
     from PIL import Image
     assert np.array_equal(np.array(Image.open(tmp_path / "eval_00000.png")), r["img_u8"].reshape(H, W, 3).cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_train_script_flow_and_resume(scenes, tmp_path):
+    """main/train.py as a function on the tiny blender scene: epochs planned from the repeat count, CustomSaver
+    checkpoints after every validation run, and setup_model(params with set_weights) resuming from one of them."""
+    import torch
+    cfg = scene_files.config_overrides("BlenderDataset", scenes["blender"], os.path.join(scenes["root"], "meta_train"),
+                                       dataset_mode="sample")
+    cfg["system"].update(steps_per_epoch=3, validation_freq=1, initial_epoch=0)
+    cfg["data"]["sample_mode"]["repeat_count"] = 1                      # 6 train images -> 6 steps -> 2 epochs
+    cfg["model"] = {"save": {"save_dir": str(tmp_path), "save_optimizer_state": True},
+                    "load": {"load_dir": str(tmp_path), "load_tag": "", "set_weights": False, "skip_optimizer": False}}
+    cfg["sampling"] = {"N_coarse": 32, "N_fine": 32, "perturb": True, "lin_inv_depth": True}
+    params = nb.load_params(cfg)
+    assert nb.train.plan_epochs(params, {"train": 6}, (scene_files.H, scene_files.W)) == (6, 3, 2)
+    nerf, hist = nb.train.launch(params, precision="bf16", seed=0)
+    assert hist.epoch == [0, 1] and len(hist.history["val_psnr_metric"]) == 2 and nerf.optimizer.iterations == 6
+    tags = sorted(f[:-len("_coarse.npz")] for f in os.listdir(tmp_path) if f.endswith("_coarse.npz"))
+    assert len(tags) == 2 and tags[0].startswith("000000_") and tags[1].startswith("000001_")
+    # resume: the reference's setup_model restores weights + optimizer when model.load.set_weights is on
+    cfg["model"]["load"].update(load_tag=tags[1], set_weights=True)
+    resumed = nb.setup_model(nb.load_params(cfg), precision="bf16", seed=123)
+    assert torch.equal(resumed.flat_params, nerf.flat_params) and resumed.optimizer.iterations == 6
+    assert torch.equal(resumed.optimizer.m, nerf.optimizer.m)
+    cfg["model"]["load"]["skip_optimizer"] = True
+    fresh_opt = nb.setup_model(nb.load_params(cfg), precision="bf16", seed=123)
+    assert torch.equal(fresh_opt.flat_params, nerf.flat_params) and fresh_opt.optimizer.iterations == 0
