@@ -30,14 +30,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// Out of line on purpose: a printf inlined into the wait loops gives every kernel a stack frame and costs the
+// MMA-issuing thread registers.
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+    printf("nerfb200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
 // Bounded wait: a protocol bug must trap (reported as a CUDA error), never hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) {
-            printf("nerfb200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
+            mbar_timeout(bar, parity);
         }
     }
 }
@@ -183,8 +188,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     long long t0 = clock64();
     while (!mbar_try_wait_cluster(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) {
-            printf("nerfb200: cluster mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
+            mbar_timeout(bar, parity);
         }
     }
 }
