@@ -246,10 +246,10 @@ def run_b200(args):
                 "traffic": traffic, "launches": mlp_n, "avg_launch_ms": mlp_ms / mlp_n,
                 "share_of_step": mlp_ms / ms_b, "traffic_note": traffic_note}
     roofline_hbm = [
-        {"kernel": "composite_fwd_kernel", "bound": "hbm", "achieved": comp_bytes / (comp_ms / 1e3) / 1e9, "peak": pk["hbm"],
+        {"kernel": "composite_fwd_kernel<2,full> + <6,full> (coarse with weights, fine without)", "bound": "hbm", "achieved": comp_bytes / (comp_ms / 1e3) / 1e9, "peak": pk["hbm"],
          "unit": "GB/s", "frac": comp_bytes / (comp_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": comp_n,
          "share_of_step": comp_ms / ms_b},
-        {"kernel": "sample_fine_kernel", "bound": "hbm", "achieved": sf_bytes / (sf_ms / 1e3) / 1e9, "peak": pk["hbm"],
+        {"kernel": "sample_fine_fast_kernel<64,128>", "bound": "hbm", "achieved": sf_bytes / (sf_ms / 1e3) / 1e9, "peak": pk["hbm"],
          "unit": "GB/s", "frac": sf_bytes / (sf_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": sf_n,
          "share_of_step": sf_ms / ms_b},
     ]

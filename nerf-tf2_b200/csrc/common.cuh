@@ -102,6 +102,43 @@ __device__ __forceinline__ float4 philox_uniform4(uint64_t seed, uint64_t ray, u
                        u32_to_unit_float(r.w));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row helpers: N consecutive floats moved as the widest vectors dividing N (the address must be
+// aligned to that vector).
+template <int N> struct VecOf;
+template <> struct VecOf<1> { using type = float; };
+template <> struct VecOf<2> { using type = float2; };
+template <> struct VecOf<4> { using type = float4; };
+// widest vector (in floats) dividing n
+__host__ __device__ constexpr int vec_width(int n) { return n % 4 == 0 ? 4 : (n % 2 == 0 ? 2 : 1); }
+
+// N consecutive floats, N*4-byte aligned groups of vec_width(N)
+template <int N>
+__device__ __forceinline__ void load_row(float (&dst)[N], const float* __restrict__ src) {
+    constexpr int V = vec_width(N);
+    using T = typename VecOf<V>::type;
+#pragma unroll
+    for (int i = 0; i < N / V; ++i) {
+        T v = *reinterpret_cast<const T*>(src + i * V);
+        const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+        for (int q = 0; q < V; ++q) dst[i * V + q] = f[q];
+    }
+}
+template <int N>
+__device__ __forceinline__ void store_row(float* __restrict__ dst, const float (&src)[N]) {
+    constexpr int V = vec_width(N);
+    using T = typename VecOf<V>::type;
+#pragma unroll
+    for (int i = 0; i < N / V; ++i) {
+        T v;
+        float* f = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int q = 0; q < V; ++q) f[q] = src[i * V + q];
+        *reinterpret_cast<T*>(dst + i * V) = v;
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,26 +11,70 @@ namespace nb {
 
 constexpr int kWarpsPerBlock = 8;
 
-template <int E>
+// Warp-cooperative copy of n floats global -> shared with cp.async (16-byte pieces when `vec`, i.e. both
+// addresses 16-byte aligned and 4 | n; 4-byte pieces otherwise). MAXN >= n is the compile-time bound the
+// vector loop is unrolled to. Completion: cp_async_wait_all + __syncwarp.
+template <int MAXN>
+__device__ __forceinline__ void warp_cp_async(float* sdst, const float* __restrict__ gsrc, int n, bool vec, int lane) {
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(sdst);
+    if (vec) {
+        const int n4 = n >> 2;
+#pragma unroll
+        for (int j = 0; j < (MAXN / 4 + 31) / 32; ++j) {
+            const int i = lane + 32 * j;
+            if (i < n4)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16u * i), "l"(gsrc + 4 * i) : "memory");
+        }
+    } else {
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s0 + 4u * i), "l"(gsrc + i) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// per-warp staging buffer, in floats: t (+1 closing value), sigma (reused for the weights), rgb
+__host__ __device__ constexpr int composite_warp_floats(int E) { return (32 * E + 4) + 32 * E + 96 * E; }
+
+// Forward. The ray's t, sigma and rgb spans are staged in shared memory with fully coalesced 16-byte
+// cp.async copies (every 32-byte sector of HBM is requested exactly once, all requests of the ray in
+// flight together); the lanes then read their E consecutive samples from shared memory with vector
+// loads (conflict-free for the strides that occur: 2, 6, 12 and 3x those). The weights go back through
+// the sigma slots and leave as coalesced 16-byte stores.
+// FULL: S == 32*E exactly (64, 128, 192, 256, 384 ... samples), every bound is a compile-time constant.
+template <int E, bool FULL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-composite_fwd_kernel(int64_t B, int S, const float* __restrict__ sigma, const float* __restrict__ rgb,
+composite_fwd_kernel(int64_t B, int S_arg, const float* __restrict__ sigma, const float* __restrict__ rgb,
                      const float* __restrict__ t_vals, int white_bg, float* __restrict__ weights,
                      float* __restrict__ pred_rgb, float* __restrict__ pred_depth, float* __restrict__ acc_map) {
+    extern __shared__ __align__(16) float comp_smem[];
     const int lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (ray >= B) return;
+    if (ray >= B) return;   // whole warp exits together; no block-level barriers below
+    float* s_t = comp_smem + (threadIdx.x >> 5) * composite_warp_floats(E);
+    float* s_sg = s_t + (32 * E + 4);
+    float* s_rgb = s_sg + 32 * E;
+    const int S = FULL ? 32 * E : S_arg;
     const int64_t base = ray * S;
     const int s0 = lane * E;
 
+    const bool vec = ((S & 3) == 0) &&
+                     ((((uintptr_t)sigma | (uintptr_t)rgb | (uintptr_t)t_vals | (uintptr_t)weights) & 15) == 0);
+    warp_cp_async<32 * E>(s_t, t_vals + base, S, vec, lane);
+    warp_cp_async<32 * E>(s_sg, sigma + base, S, vec, lane);
+    warp_cp_async<96 * E>(s_rgb, rgb + 3 * base, 3 * S, vec, lane);
+    cp_async_wait_all();
+    __syncwarp();
+
     float t[E + 1], sg[E];
+    {
+        float tt[E];
+        load_row<E>(tt, s_t + s0);
+        load_row<E>(sg, s_sg + s0);
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        int s = s0 + e;
-        t[e] = s < S ? __ldg(t_vals + base + s) : 0.f;
-        sg[e] = s < S ? __ldg(sigma + base + s) : 0.f;
+        for (int e = 0; e < E; ++e) t[e] = tt[e];
+        t[E] = s_t[s0 + E];   // first t of the next lane closes this lane's last interval (unused past S-1)
     }
-    // first t of the next lane closes this lane's last interval
-    t[E] = __shfl_down_sync(0xffffffffu, t[0], 1);
 
     float alpha[E], f[E];
     float lane_prod = 1.f;
@@ -55,22 +99,38 @@ composite_fwd_kernel(int64_t B, int S, const float* __restrict__ sigma, const fl
     if (lane == 0) T = 1.f;
 
     float cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
+    float c[3 * E], wv[E];
+    load_row<3 * E>(c, s_rgb + 3 * s0);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         int s = s0 + e;
         float w = alpha[e] * T;
         T *= f[e];
+        wv[e] = w;
         if (s < S) {
-            if (weights) weights[base + s] = w;
-            const float* c = rgb + 3 * (base + s);
-            cr += w * __ldg(c + 0);
-            cg += w * __ldg(c + 1);
-            cb += w * __ldg(c + 2);
+            cr += w * c[3 * e + 0];
+            cg += w * c[3 * e + 1];
+            cb += w * c[3 * e + 2];
             dep += w * t[e];
             acc += w;
         }
     }
+    if (weights) store_row<E>(s_sg + s0, wv);   // this lane's own slots: already consumed above
     cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dep = warp_sum(dep); acc = warp_sum(acc);
+    if (weights) {
+        __syncwarp();
+        float* wout = weights + base;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < (8 * E + 31) / 32; ++j) {
+                const int i = lane + 32 * j;
+                if (i < (S >> 2)) reinterpret_cast<float4*>(wout)[i] = reinterpret_cast<const float4*>(s_sg)[i];
+            }
+        } else {
+#pragma unroll 1
+            for (int i = lane; i < S; i += 32) wout[i] = s_sg[i];
+        }
+    }
     if (lane == 0) {
         if (white_bg) {                                                            // :542-544
             float bg = __fsub_rn(1.f, acc);
@@ -194,8 +254,18 @@ int nerfb200_composite_fwd(int64_t B, int S, const float* sigma, const float* rg
     if (B == 0) return 0;
     NB_CHECK_ARG(sigma && rgb && t_vals && pred_rgb && pred_depth && acc_map, "composite_fwd: NULL pointer");
     unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    NB_DISPATCH_E(pick_E(S), (composite_fwd_kernel<E><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-                                 B, S, sigma, rgb, t_vals, white_bg, weights, pred_rgb, pred_depth, acc_map)));
+    NB_DISPATCH_E(pick_E(S), {
+        constexpr int smem = kWarpsPerBlock * composite_warp_floats(E) * (int)sizeof(float);
+        if (S == 32 * E) {
+            if (smem > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            composite_fwd_kernel<E, true><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+                B, S, sigma, rgb, t_vals, white_bg, weights, pred_rgb, pred_depth, acc_map);
+        } else {
+            if (smem > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            composite_fwd_kernel<E, false><<<grid, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+                B, S, sigma, rgb, t_vals, white_bg, weights, pred_rgb, pred_depth, acc_map);
+        }
+    });
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -216,6 +216,316 @@ sample_fine_kernel(int64_t B, int Nc, const float* __restrict__ bin_weights, con
     for (int k = lane; k < S; k += 32) t_sorted[ray * S + k] = s_out[k];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path for the shapes the reference is run at (N_coarse a power of two: 64/128 and 128/256).
+// Same pdf/cdf/search/inversion arithmetic as above; what changes is how the ascending concat is
+// produced. The register bitonic network + two rank-merge searches (≈1.2 k warp instructions per ray)
+// are replaced by a placement that is linear in the number of samples:
+//   * fine samples: bucket by floor(u*Nf) (u is i.i.d. uniform, so bucket occupancy is Poisson(1)
+//     whatever the pdf looks like), smem-atomic arrival slots, one exclusive scan of the Nf counters,
+//     rank inside the (tiny) bucket by direct comparison of t;
+//   * number of coarse samples below a fine sample: its bin index plus one compare (each bin holds
+//     exactly one coarse sample);
+//   * coarse samples: the slots the fine samples left empty, in order.
+// t is monotone in u only up to fp32 rounding across bin boundaries, and t_coarse is caller data, so
+// the placement is CHECKED (no empty slot left, output ascending) and a warp whose check fails redoes
+// the ray with the generic full bitonic sort: the result is always the exact sort.
+constexpr uint32_t kHoleBits = 0xFFFFFFFFu;   // a NaN pattern no sample can carry through the check
+
+template <int NC, int NF>
+struct alignas(16) FastWarpSmem {
+    static constexpr int S = NC + NF;
+    static constexpr int P2 = (S <= 256) ? 256 : ((S <= 512) ? 512 : 1024);
+    float out[P2];        // merged samples (the generic fallback sorts the padded concat here)
+    float tc[NC];         // coarse samples
+    float tmp[NF];        // fine samples in bucket order
+    int cnt[NF];          // u-bucket occupancy
+    int base[NF];         // (exclusive prefix of cnt) << 16 | cnt
+    float pdf[NC];
+    float edges[NC + 4];
+    // cdf[k] lives at word k + (k >> 5): entries k and k+32 fall into different banks, which makes every step
+    // of the lock-step binary search conflict-free (step j only ever reads entries that differ by multiples of 2^(j+1))
+    float cdf[NC + NC / 32 + 4];
+};
+__host__ __device__ constexpr int cdf_slot(int k) { return k + (k >> 5); }
+
+template <int NC, int NF>
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+sample_fine_fast_kernel(int64_t B, const float* __restrict__ bin_weights, const float* __restrict__ bin_edges,
+                        const float* __restrict__ t_coarse, const float* __restrict__ u_fine, uint64_t seed,
+                        int64_t ray0, float* __restrict__ t_sorted, int32_t* __restrict__ piece_idxs,
+                        float* __restrict__ cdf_out, float* __restrict__ t_fine_out) {
+    static_assert((NC & (NC - 1)) == 0 && NC >= 32, "fast path: N_coarse must be a power of two");
+    static_assert((NF & (NF - 1)) == 0 && NF >= 128, "fast path: N_fine must be a power of two >= 128");
+    constexpr int EC = NC / 32, EF = NF / 32, S = NC + NF, ES = S / 32;
+    static_assert(S % 32 == 0 && ES % 2 == 0, "fast path: 32 | (Nc+Nf)");
+    using Smem = FastWarpSmem<NC, NF>;
+    constexpr int P2 = Smem::P2;
+    __shared__ Smem sm_all[kSamplerWarps];
+    constexpr unsigned FULL = 0xffffffffu;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ray = (int64_t)blockIdx.x * kSamplerWarps + warp;
+    if (ray >= B) return;   // whole warp exits together; no block-level barriers below
+    Smem& sm = sm_all[warp];
+
+    // ---- loads: everything this ray needs from HBM is requested before the first use
+    float w[EC], tcv[EC], u[EF];
+    load_row<EC>(w, bin_weights + ray * NC + lane * EC);
+    load_row<EC>(tcv, t_coarse + ray * NC + lane * EC);
+    {
+        const float* ep = bin_edges + ray * (NC + 1);    // rows of Nc+1 floats: not vector-aligned
+        float ev[EC];
+#pragma unroll
+        for (int j = 0; j < EC; ++j) ev[j] = __ldg(ep + lane + 32 * j);
+        if (lane == 0) sm.edges[NC] = __ldg(ep + NC);
+#pragma unroll
+        for (int j = 0; j < EC; ++j) sm.edges[lane + 32 * j] = ev[j];
+    }
+    if (u_fine) {
+        load_row<EF>(u, u_fine + ray * NF + lane * EF);
+    } else {
+#pragma unroll
+        for (int e0 = 0; e0 < EF; e0 += 4) {
+            float4 r = philox_uniform4(seed, (uint64_t)(ray0 + ray), (uint32_t)((lane * EF + e0) >> 2), 1u);
+            u[e0] = r.x; u[e0 + 1] = r.y; u[e0 + 2] = r.z; u[e0 + 3] = r.w;
+        }
+    }
+    store_row<EC>(sm.tc + lane * EC, tcv);
+    {
+        float z[EF];
+#pragma unroll
+        for (int e = 0; e < EF; ++e) z[e] = 0.f;       // int 0 == float +0 bit pattern
+        store_row<EF>(reinterpret_cast<float*>(sm.cnt) + lane * EF, z);
+        float h[ES];
+#pragma unroll
+        for (int j = 0; j < ES; ++j) h[j] = __uint_as_float(kHoleBits);
+        store_row<ES>(sm.out + lane * ES, h);
+    }
+    __syncwarp();
+
+    // ---- pdf / cdf (utils/ray_utils.py:335-345); identical arithmetic and summation order to the generic kernel
+    float pv[EC], width[EC];
+    {
+        float ed[EC + 1];
+#pragma unroll
+        for (int e = 0; e <= EC; ++e) ed[e] = sm.edges[lane * EC + e];
+        float local = 0.f;
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+            w[e] = __fadd_rn(w[e], 1e-5f);
+            width[e] = __fsub_rn(ed[e + 1], ed[e]);
+            local = __fadd_rn(local, __fmul_rn(w[e], width[e]));
+        }
+        float denom = local;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) denom = __fadd_rn(denom, __shfl_xor_sync(FULL, denom, o));
+        float run = 0.f, cl[EC];
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+            pv[e] = __fdiv_rn(w[e], denom);
+            run = __fadd_rn(run, __fmul_rn(pv[e], width[e]));
+            cl[e] = run;
+        }
+        float incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            float v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl = __fadd_rn(incl, v);
+        }
+        float excl = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) excl = 0.f;
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+            sm.cdf[cdf_slot(lane * EC + e + 1)] = __fadd_rn(excl, cl[e]);
+            sm.pdf[lane * EC + e] = pv[e];
+        }
+        if (lane == 0) sm.cdf[0] = 0.f;
+    }
+    __syncwarp();
+    if (cdf_out)
+        for (int k = lane; k <= NC; k += 32) cdf_out[ray * (NC + 1) + k] = sm.cdf[cdf_slot(k)];
+
+    // ---- searchsorted(side='right') over the NC-1 inner edges cdf[1..NC-1] + inversion (:363-376)
+    int idx[EF];
+    float tf[EF];
+    {
+        // number of inner edges <= u; NC-1 = 2^k - 1 edges, so no bound checks. Byte-address form (one LDS with an
+        // immediate offset, one compare, two conditional moves per step), the EF searches of a lane interleaved.
+        // The last edge that compared <= u IS cdf[idx] (cdf[0] = 0), so the cdf gather of the inversion is free.
+        const uint32_t cdf0 = (uint32_t)__cvta_generic_to_shared(sm.cdf);
+        uint32_t a[EF];
+        float cleft[EF];
+#pragma unroll
+        for (int e = 0; e < EF; ++e) { a[e] = cdf0; cleft[e] = 0.f; }
+#pragma unroll
+        for (int step = NC / 2; step > 0; step >>= 1) {
+            const uint32_t off = 4u * (uint32_t)cdf_slot(step);
+#pragma unroll
+            for (int e = 0; e < EF; ++e) {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a[e] + off) : "memory");
+                const bool take = v <= u[e];
+                a[e] += take ? off : 0u;
+                cleft[e] = take ? v : cleft[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < EF; ++e) {
+            const uint32_t wd = (a[e] - cdf0) >> 2;        // = idx + idx/32
+            const int pos = (int)(wd - wd / 33u);
+            idx[e] = pos;
+            float p = sm.pdf[pos];
+            const float mask = p < 1e-8f ? 0.f : 1.f;
+            p = fmaxf(p, 1e-8f);
+            tf[e] = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(u[e], cleft[e]), p), mask), sm.edges[pos]);
+        }
+    }
+    if (piece_idxs) {
+#pragma unroll
+        for (int e = 0; e < EF; ++e) piece_idxs[ray * NF + lane * EF + e] = idx[e];
+    }
+    if (t_fine_out) store_row<EF>(t_fine_out + ray * NF + lane * EF, tf);
+
+    // ---- is t_coarse ascending? (it is when it comes from the stratified sampler)
+    bool ok = true;
+    {
+        const float nxt = __shfl_down_sync(FULL, tcv[0], 1);
+#pragma unroll
+        for (int e = 0; e + 1 < EC; ++e) ok = ok && (tcv[e] <= tcv[e + 1]);
+        if (lane < 31) ok = ok && (tcv[EC - 1] <= nxt);
+    }
+    if (__all_sync(FULL, ok)) {
+        // ---- fine samples: rank = (#fine in lower u-buckets) + (rank by t inside the bucket)
+        int key[EF], slot[EF];
+#pragma unroll
+        for (int e = 0; e < EF; ++e) {
+            int k = (int)(u[e] * (float)NF);
+            k = min(max(k, 0), NF - 1);
+            key[e] = k;
+            slot[e] = atomicAdd(&sm.cnt[k], 1);
+        }
+        __syncwarp();
+        int excl, M;
+        {
+            int c[EF], loc = 0, cmax = 0;
+#pragma unroll
+            for (int e = 0; e < EF; ++e) c[e] = sm.cnt[lane * EF + e];
+            int ex[EF];
+#pragma unroll
+            for (int e = 0; e < EF; ++e) { ex[e] = loc; loc += c[e]; cmax = max(cmax, c[e]); }
+            int incl = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            excl = incl - loc;
+#pragma unroll
+            for (int e = 0; e < EF; ++e) sm.base[lane * EF + e] = ((excl + ex[e]) << 16) | c[e];
+            M = __reduce_max_sync(FULL, cmax);
+        }
+        __syncwarp();
+        int b[EF], n[EF], r[EF];
+#pragma unroll
+        for (int e = 0; e < EF; ++e) {
+            const int bc = sm.base[key[e]];
+            b[e] = bc >> 16;
+            n[e] = bc & 0xffff;
+            r[e] = 0;
+            sm.tmp[b[e] + slot[e]] = tf[e];
+        }
+        __syncwarp();
+        // rank inside the bucket: compare with the OTHER members only. The load is predicated (s-th member exists and
+        // is not this sample), so lanes whose bucket is exhausted put no traffic on the shared-memory pipe; an
+        // unloaded `o` stays NaN and compares false both ways.
+        const uint32_t tmp0 = (uint32_t)__cvta_generic_to_shared(sm.tmp);
+        for (int s = 0; s < M; ++s) {
+#pragma unroll
+            for (int e = 0; e < EF; ++e) {
+                float o = __uint_as_float(0x7fc00000u);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.lt.s32 p, %2, %3;\n\t"
+                    "setp.ne.and.s32 p, %2, %4, p;\n\t"
+                    "@p ld.shared.f32 %0, [%1];\n\t}"
+                    : "+f"(o)
+                    : "r"(tmp0 + 4u * (uint32_t)(b[e] + s)), "r"(s), "r"(n[e]), "r"(slot[e])
+                    : "memory");
+                r[e] += ((o < tf[e]) | ((o == tf[e]) & (s < slot[e]))) ? 1 : 0;
+            }
+        }
+        // ---- merged position = fine rank + #coarse below; bin idx holds exactly one coarse sample
+#pragma unroll
+        for (int e = 0; e < EF; ++e) {
+            const int below = idx[e] + (sm.tc[idx[e]] < tf[e] ? 1 : 0);
+            sm.out[b[e] + r[e] + below] = tf[e];
+        }
+        __syncwarp();
+        // ---- coarse samples fill the empty slots in order; then verify
+        float ov[ES];
+        load_row<ES>(ov, sm.out + lane * ES);
+        int h = 0;
+#pragma unroll
+        for (int j = 0; j < ES; ++j) h += (__float_as_uint(ov[j]) == kHoleBits) ? 1 : 0;
+        int hin = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULL, hin, o);
+            if (lane >= o) hin += v;
+        }
+        const int total = __shfl_sync(FULL, hin, 31);
+        if (total == NC) {   // warp-uniform
+            int hp = hin - h;      // < NC wherever a hole is left, because total == NC
+            const uint32_t tc0 = (uint32_t)__cvta_generic_to_shared(sm.tc);
+#pragma unroll
+            for (int j = 0; j < ES; ++j) {     // predicated load: only the lanes that own a hole read
+                const uint32_t hole = (__float_as_uint(ov[j]) == kHoleBits) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ne.u32 p, %2, 0;\n\t"
+                    "@p ld.shared.f32 %0, [%1];\n\t}"
+                    : "+f"(ov[j])
+                    : "r"(tc0 + 4u * (uint32_t)hp), "r"(hole)
+                    : "memory");
+                hp += (int)hole;
+            }
+            const float nxt = __shfl_down_sync(FULL, ov[0], 1);
+            bool asc = true;
+#pragma unroll
+            for (int j = 0; j + 1 < ES; ++j) asc = asc && (ov[j] <= ov[j + 1]);
+            if (lane < 31) asc = asc && (ov[ES - 1] <= nxt);
+            if (__all_sync(FULL, asc)) {
+                store_row<ES>(t_sorted + ray * S + lane * ES, ov);
+                return;
+            }
+        }
+    }
+    // ---- generic path (t_coarse not ascending, or the placement check failed): bitonic sort of the
+    // padded concat in shared memory
+    __syncwarp();
+    for (int k = lane; k < NC; k += 32) sm.out[k] = sm.tc[k];
+#pragma unroll
+    for (int e = 0; e < EF; ++e) sm.out[NC + lane * EF + e] = tf[e];
+    for (int k = S + lane; k < P2; k += 32) sm.out[k] = __int_as_float(0x7f800000);
+    __syncwarp();
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < P2; i += 32) {
+                int p = i ^ j;
+                if (p > i) {
+                    float a = sm.out[i], c = sm.out[p];
+                    bool up = (i & k) == 0;
+                    if ((a > c) == up) { sm.out[i] = c; sm.out[p] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    for (int k = lane; k < S; k += 32) t_sorted[ray * S + k] = sm.out[k];
+}
+
 }  // namespace nb
 
 using namespace nb;
@@ -236,11 +546,25 @@ int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights, co
     }
     if (B == 0) return 0;
     NB_CHECK_ARG(bin_weights && bin_edges && t_coarse && t_sorted, "sample_fine: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    // fast path: the reference's shapes, vector-aligned rows (cudaMalloc'd tensors always are)
+    const bool aligned = (((uintptr_t)bin_weights | (uintptr_t)t_coarse | (uintptr_t)t_sorted | (uintptr_t)u_fine |
+                           (uintptr_t)t_fine) & 15) == 0;
+    if (aligned && ((Nc == 64 && Nf == 128) || (Nc == 128 && Nf == 256))) {
+        unsigned g = (unsigned)((B + kSamplerWarps - 1) / kSamplerWarps);
+        if (Nc == 64)
+            sample_fine_fast_kernel<64, 128><<<g, kSamplerWarps * 32, 0, st>>>(B, bin_weights, bin_edges, t_coarse, u_fine,
+                                                                               seed, ray0, t_sorted, piece_idxs, cdf, t_fine);
+        else
+            sample_fine_fast_kernel<128, 256><<<g, kSamplerWarps * 32, 0, st>>>(B, bin_weights, bin_edges, t_coarse, u_fine,
+                                                                                seed, ray0, t_sorted, piece_idxs, cdf, t_fine);
+        NB_LAUNCH_CHECK();
+        return 0;
+    }
     int S = Nc + Nf, P2 = 1;
     while (P2 < S) P2 <<= 1;
     size_t smem = (size_t)kSamplerWarps * ((Nc + 1) * 2 + Nc * 2 + Nf + P2) * sizeof(float);
     unsigned grid = (unsigned)((B + kSamplerWarps - 1) / kSamplerWarps);
-    cudaStream_t st = (cudaStream_t)stream;
 #define NB_LAUNCH_SF(EFv)                                                                                      \
     do {                                                                                                       \
         if (smem > 48 * 1024)                                                                                  \

@@ -215,3 +215,104 @@ def test_positional_encoding_and_depth_map(golden):
         ref = rm.create_depth_map(depth, 9, 11, 0.2125, mt, v["K"], v["c2w"])
         out = ru.create_depth_map(dev(depth), 9, 11, 0.2125, mt, v["K"], v["c2w"])
         assert np.allclose(host(out), ref, rtol=2e-6, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# The placement fast path of the fine sampler (N_coarse/N_fine = 64/128 and 128/256): whatever the
+# inputs, t_sorted must be the exact ascending sort of concat(t_coarse, t_fine) and the indices the
+# exact upper bounds in the kernel's own CDF. Cases chosen to hit the self-check's fallback too.
+def _fast_sampler_case(Nc, Nf, w, u, t_c=None, edges=None, seed=0):
+    B = w.shape[0]
+    rng = np.random.default_rng(seed)
+    if edges is None:
+        near = np.full((B, 1), 0.425, F32); far = np.full((B, 1), 1.275, F32)
+        o = rm.create_input_batch_coarse_model(Nc, True, True, np.zeros((B, 3), F32), np.ones((B, 3), F32), near, far,
+                                               rng.random((B, Nc), dtype=F32))
+        edges = o["bin_data"]["bin_edges"]
+        if t_c is None:
+            t_c = o["t_vals"]
+    ts, dbg = ru.sample_fine(Nf, dev(w), dev(edges), dev(t_c), dev(u), debug=True)
+    ts, cdf, idx, tf = host(ts), host(dbg["cdf"]), host(dbg["piece_idxs"]), host(dbg["t_vals_fine"])
+    assert np.array_equal(idx, rm.searchsorted_right(cdf[:, 1:-1], u))
+    assert np.array_equal(ts, np.sort(np.concatenate([t_c, tf], axis=1), axis=1))
+    # without the debug outputs the kernel takes the same path and returns the same samples
+    assert np.array_equal(host(ru.sample_fine(Nf, dev(w), dev(edges), dev(t_c), dev(u))), ts)
+    return ts, tf, idx
+
+
+@pytest.mark.parametrize("Nc,Nf", [(64, 128), (128, 256)])
+def test_fine_sampler_fast_path_bulk_exact(Nc, Nf):
+    rng = np.random.default_rng(Nc)
+    B = 4099                                            # not a multiple of the warps per CTA
+    sharp = rng.choice([1, 4, 16, 64], size=(B, 1)).astype(F32)
+    w = (rng.random((B, Nc), dtype=F32) ** sharp).astype(F32)      # flat ... nearly one-hot pdfs
+    w[rng.random((B, Nc)) < 0.3] = 0.0                             # empty space (sigma == 0 for most samples)
+    u = rng.random((B, Nf), dtype=F32)
+    _fast_sampler_case(Nc, Nf, w, u, seed=1)
+
+
+@pytest.mark.parametrize("Nc,Nf", [(64, 128), (128, 256)])
+def test_fine_sampler_fast_path_adversarial(Nc, Nf):
+    rng = np.random.default_rng(7)
+    B = 24
+    w = rng.random((B, Nc), dtype=F32)
+    u = rng.random((B, Nf), dtype=F32)
+    one_m = np.nextafter(F32(1), F32(0))
+    u[0] = 0.0                                # every sample in one u-bucket, all t equal (ties by arrival slot)
+    u[1] = 0.5
+    u[2] = one_m                              # beyond cdf_last: last bin, t may pass `far` by ulps
+    u[3] = np.sort(u[3]); u[4] = np.sort(u[4])[::-1]
+    u[5, ::2] = u[5, 1::2]                    # duplicate pairs
+    u[6] = (np.arange(Nf, dtype=F32) / F32(Nf))            # exactly on the bucket boundaries
+    u[7] = np.repeat(rng.random(Nf // 8, dtype=F32), 8)    # 8-fold duplicates
+    w[8] = 0.0                                # uniform pdf
+    w[9] = 0.0; w[9, 5] = 1.0                 # one-hot: almost every sample in one bin
+    w[10] = 0.0; w[10, Nc - 1] = 1e6          # pdf < 1e-8 elsewhere: masked inversion returns the left edge
+    w[11] = 0.0; w[11, 0] = 1e6; u[11, :Nf // 2] = one_m   # ... with half the samples landing in masked bins
+    w[12] = 1e-12
+    _fast_sampler_case(Nc, Nf, w, u, seed=2)
+    # coarse samples sitting exactly on the bin edges: ties between a coarse and a fine sample
+    near = np.full((B, 1), 0.4, F32); far = np.full((B, 1), 1.2, F32)
+    edges = rm.tf_linspace(near, far, Nc + 1)
+    for t_c in (edges[:, :-1].copy(), edges[:, 1:].copy()):
+        uu = rng.random((B, Nf), dtype=F32)
+        uu[:, :8] = 0.0
+        _fast_sampler_case(Nc, Nf, w, uu, t_c=t_c, edges=edges)
+    # duplicate coarse samples (still ascending) and a descending row (generic path) in the same launch
+    t_c = np.repeat(edges[:, :-1:2], 2, axis=1).copy()
+    t_c[3] = t_c[3, ::-1]
+    _fast_sampler_case(Nc, Nf, w, rng.random((B, Nf), dtype=F32), t_c=t_c, edges=edges)
+
+
+def test_fine_sampler_unaligned_rows_take_the_generic_kernel():
+    rng = np.random.default_rng(11)
+    B, Nc, Nf = 33, 64, 128
+    edges = rm.tf_linspace(np.full((B, 1), 0.4, F32), np.full((B, 1), 1.2, F32), Nc + 1)
+    tc = F32(0.5) * (edges[:, :-1] + edges[:, 1:])
+    w = rng.random((B, Nc), dtype=F32); u = rng.random((B, Nf), dtype=F32)
+    a = ru.sample_fine(Nf, dev(w), dev(edges), dev(tc), dev(u))
+    # same data at a 4-byte-offset address: not vector-aligned
+    wbuf = torch.empty(B * Nc + 1, dtype=torch.float32, device="cuda")
+    wbuf[1:] = dev(w).reshape(-1)
+    b = ru.sample_fine(Nf, wbuf[1:].view(B, Nc), dev(edges), dev(tc), dev(u))
+    assert torch.equal(a, b)
+
+
+def test_integrator_unaligned_and_short_batches():
+    rng = np.random.default_rng(12)
+    for S in (64, 192):
+        for B in (1, 7, 8, 9, 1025):
+            t = np.sort(rng.random((B, S), dtype=F32) * F32(0.8) + F32(0.4), axis=1)
+            sig = (rng.random((B * S,), dtype=F32) * 20 * (rng.random((B * S,)) > 0.5)).astype(F32)
+            rgb = rng.random((B * S, 3), dtype=F32)
+            a = ru.post_process_model_output(dev(rgb), dev(sig), dev(t), True)
+            if B == 1025:
+                o = rm.post_process_model_output(rgb, sig[:, None], t, True)
+                for k in ("weights", "pred_rgb", "pred_depth", "acc_map"):
+                    assert np.allclose(host(a[k]), o[k], rtol=5e-5, atol=3e-6), k
+            # the same rows at addresses that are not 16-byte aligned: scalar staging, identical results
+            sbuf = torch.empty(B * S + 1, dtype=torch.float32, device="cuda"); sbuf[1:] = dev(sig)
+            rbuf = torch.empty(B * S * 3 + 3, dtype=torch.float32, device="cuda"); rbuf[3:] = dev(rgb).reshape(-1)
+            b = ru.post_process_model_output(rbuf[3:].view(B * S, 3), sbuf[1:], dev(t), True)
+            for k in ("weights", "pred_rgb", "pred_depth", "acc_map"):
+                assert torch.equal(a[k], b[k]), (S, B, k)
