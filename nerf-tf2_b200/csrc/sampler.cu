@@ -233,15 +233,15 @@ sample_fine_kernel(int64_t B, int Nc, const float* __restrict__ bin_weights, con
 // the ray with the generic full bitonic sort: the result is always the exact sort.
 constexpr uint32_t kHoleBits = 0xFFFFFFFFu;   // a NaN pattern no sample can carry through the check
 
-template <int NC, int NF>
+template <int NC, int NF, bool SORTED>
 struct alignas(16) FastWarpSmem {
     static constexpr int S = NC + NF;
     static constexpr int P2 = (S <= 256) ? 256 : ((S <= 512) ? 512 : 1024);
     float out[P2];        // merged samples (the generic fallback sorts the padded concat here)
     float tc[NC];         // coarse samples
-    float tmp[NF];        // fine samples in bucket order
-    int cnt[NF];          // u-bucket occupancy
-    int base[NF];         // (exclusive prefix of cnt) << 16 | cnt
+    float tmp[SORTED ? 4 : NF];        // fine samples in bucket order       (explicit-u variant only)
+    int cnt[SORTED ? 4 : NF];          // u-bucket occupancy
+    int base[SORTED ? 4 : NF];         // (exclusive prefix of cnt) << 16 | cnt
     float pdf[NC];
     float edges[NC + 4];
     // cdf[k] lives at word k + (k >> 5): entries k and k+32 fall into different banks, which makes every step
@@ -250,7 +250,7 @@ struct alignas(16) FastWarpSmem {
 };
 __host__ __device__ constexpr int cdf_slot(int k) { return k + (k >> 5); }
 
-template <int NC, int NF>
+template <int NC, int NF, bool SORTED>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_fine_fast_kernel(int64_t B, const float* __restrict__ bin_weights, const float* __restrict__ bin_edges,
                         const float* __restrict__ t_coarse, const float* __restrict__ u_fine, uint64_t seed,
@@ -260,7 +260,7 @@ sample_fine_fast_kernel(int64_t B, const float* __restrict__ bin_weights, const 
     static_assert((NF & (NF - 1)) == 0 && NF >= 128, "fast path: N_fine must be a power of two >= 128");
     constexpr int EC = NC / 32, EF = NF / 32, S = NC + NF, ES = S / 32;
     static_assert(S % 32 == 0 && ES % 2 == 0, "fast path: 32 | (Nc+Nf)");
-    using Smem = FastWarpSmem<NC, NF>;
+    using Smem = FastWarpSmem<NC, NF, SORTED>;
     constexpr int P2 = Smem::P2;
     __shared__ Smem sm_all[kSamplerWarps];
     constexpr unsigned FULL = 0xffffffffu;
@@ -283,21 +283,54 @@ sample_fine_fast_kernel(int64_t B, const float* __restrict__ bin_weights, const 
 #pragma unroll
         for (int j = 0; j < EC; ++j) sm.edges[lane + 32 * j] = ev[j];
     }
-    if (u_fine) {
+    if constexpr (!SORTED) {
         load_row<EF>(u, u_fine + ray * NF + lane * EF);
     } else {
+        // No uniforms given: the reference draws NF i.i.d. U[0,1) per ray and sorts the samples they produce
+        // (ray_utils.py:355,385). Their order statistics are generated directly instead - normalised partial sums of
+        // NF+1 i.i.d. exponentials (Renyi's representation: same joint distribution) - so u arrives ascending across
+        // (lane, e) and nothing has to be sorted. Philox counters as everywhere: (global ray id, block of 4, stream 1).
+        float c[EF], extra = 0.f;
 #pragma unroll
         for (int e0 = 0; e0 < EF; e0 += 4) {
-            float4 r = philox_uniform4(seed, (uint64_t)(ray0 + ray), (uint32_t)((lane * EF + e0) >> 2), 1u);
-            u[e0] = r.x; u[e0 + 1] = r.y; u[e0 + 2] = r.z; u[e0 + 3] = r.w;
+            const uint64_t gr = (uint64_t)(ray0 + ray);
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)gr, (uint32_t)(gr >> 32), (uint32_t)((lane * EF + e0) >> 2), 1u),
+                                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)   // v in (0,1] from the top 24 bits; -log2 v >= 0 (the log base cancels below)
+                c[e0 + q] = -__log2f((float)((wd[q] >> 8) + 1u) * 5.9604644775390625e-8f);
+            if (e0 == 0)                  // the (NF+1)-th exponential from the bits not used above (lane 31's is taken)
+                extra = -__log2f((float)(((r.x & 0xffu) | ((r.y & 0xffu) << 8) | ((r.z & 0xffu) << 16)) + 1u) * 5.9604644775390625e-8f);
+        }
+#pragma unroll
+        for (int e = 1; e < EF; ++e) c[e] += c[e - 1];
+        float incl = c[EF - 1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        float excl = __shfl_up_sync(FULL, incl, 1);
+        if (lane == 0) excl = 0.f;
+        const float total = fmaxf(__shfl_sync(FULL, incl, 31) + __shfl_sync(FULL, extra, 31), 1e-30f);
+        const float inv = __frcp_rn(total);
+#pragma unroll
+        for (int e = 0; e < EF; ++e) {
+            // partial sum; the lane's last one IS the scan value the next lane starts from, the others are capped by
+            // it, so the sequence is non-decreasing whatever the rounding of the tree scan
+            const float part = (e == EF - 1) ? incl : fminf(excl + c[e], incl);
+            u[e] = fminf(part * inv, 0.99999994f);
         }
     }
     store_row<EC>(sm.tc + lane * EC, tcv);
     {
-        float z[EF];
+        if constexpr (!SORTED) {
+            float z[EF];
 #pragma unroll
-        for (int e = 0; e < EF; ++e) z[e] = 0.f;       // int 0 == float +0 bit pattern
-        store_row<EF>(reinterpret_cast<float*>(sm.cnt) + lane * EF, z);
+            for (int e = 0; e < EF; ++e) z[e] = 0.f;       // int 0 == float +0 bit pattern
+            store_row<EF>(reinterpret_cast<float*>(sm.cnt) + lane * EF, z);
+        }
         float h[ES];
 #pragma unroll
         for (int j = 0; j < ES; ++j) h[j] = __uint_as_float(kHoleBits);
@@ -397,70 +430,79 @@ sample_fine_fast_kernel(int64_t B, const float* __restrict__ bin_weights, const 
         if (lane < 31) ok = ok && (tcv[EC - 1] <= nxt);
     }
     if (__all_sync(FULL, ok)) {
-        // ---- fine samples: rank = (#fine in lower u-buckets) + (rank by t inside the bucket)
-        int key[EF], slot[EF];
+        int frank[EF];   // rank of the sample among the fine samples
+        if constexpr (SORTED) {
+            // u ascending => t ascending, up to rounding across bin boundaries (checked below)
 #pragma unroll
-        for (int e = 0; e < EF; ++e) {
-            int k = (int)(u[e] * (float)NF);
-            k = min(max(k, 0), NF - 1);
-            key[e] = k;
-            slot[e] = atomicAdd(&sm.cnt[k], 1);
-        }
-        __syncwarp();
-        int excl, M;
-        {
-            int c[EF], loc = 0, cmax = 0;
-#pragma unroll
-            for (int e = 0; e < EF; ++e) c[e] = sm.cnt[lane * EF + e];
-            int ex[EF];
-#pragma unroll
-            for (int e = 0; e < EF; ++e) { ex[e] = loc; loc += c[e]; cmax = max(cmax, c[e]); }
-            int incl = loc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            excl = incl - loc;
-#pragma unroll
-            for (int e = 0; e < EF; ++e) sm.base[lane * EF + e] = ((excl + ex[e]) << 16) | c[e];
-            M = __reduce_max_sync(FULL, cmax);
-        }
-        __syncwarp();
-        int b[EF], n[EF], r[EF];
-#pragma unroll
-        for (int e = 0; e < EF; ++e) {
-            const int bc = sm.base[key[e]];
-            b[e] = bc >> 16;
-            n[e] = bc & 0xffff;
-            r[e] = 0;
-            sm.tmp[b[e] + slot[e]] = tf[e];
-        }
-        __syncwarp();
-        // rank inside the bucket: compare with the OTHER members only. The load is predicated (s-th member exists and
-        // is not this sample), so lanes whose bucket is exhausted put no traffic on the shared-memory pipe; an
-        // unloaded `o` stays NaN and compares false both ways.
-        const uint32_t tmp0 = (uint32_t)__cvta_generic_to_shared(sm.tmp);
-        for (int s = 0; s < M; ++s) {
-#pragma unroll
+            for (int e = 0; e < EF; ++e) frank[e] = lane * EF + e;
+        } else {
+            // ---- fine samples: rank = (#fine in lower u-buckets) + (rank by t inside the bucket)
+            int key[EF], slot[EF];
+    #pragma unroll
             for (int e = 0; e < EF; ++e) {
-                float o = __uint_as_float(0x7fc00000u);
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "setp.lt.s32 p, %2, %3;\n\t"
-                    "setp.ne.and.s32 p, %2, %4, p;\n\t"
-                    "@p ld.shared.f32 %0, [%1];\n\t}"
-                    : "+f"(o)
-                    : "r"(tmp0 + 4u * (uint32_t)(b[e] + s)), "r"(s), "r"(n[e]), "r"(slot[e])
-                    : "memory");
-                r[e] += ((o < tf[e]) | ((o == tf[e]) & (s < slot[e]))) ? 1 : 0;
+                int k = (int)(u[e] * (float)NF);
+                k = min(max(k, 0), NF - 1);
+                key[e] = k;
+                slot[e] = atomicAdd(&sm.cnt[k], 1);
             }
+            __syncwarp();
+            int excl, M;
+            {
+                int c[EF], loc = 0, cmax = 0;
+    #pragma unroll
+                for (int e = 0; e < EF; ++e) c[e] = sm.cnt[lane * EF + e];
+                int ex[EF];
+    #pragma unroll
+                for (int e = 0; e < EF; ++e) { ex[e] = loc; loc += c[e]; cmax = max(cmax, c[e]); }
+                int incl = loc;
+    #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                excl = incl - loc;
+    #pragma unroll
+                for (int e = 0; e < EF; ++e) sm.base[lane * EF + e] = ((excl + ex[e]) << 16) | c[e];
+                M = __reduce_max_sync(FULL, cmax);
+            }
+            __syncwarp();
+            int b[EF], n[EF], r[EF];
+    #pragma unroll
+            for (int e = 0; e < EF; ++e) {
+                const int bc = sm.base[key[e]];
+                b[e] = bc >> 16;
+                n[e] = bc & 0xffff;
+                r[e] = 0;
+                sm.tmp[b[e] + slot[e]] = tf[e];
+            }
+            __syncwarp();
+            // rank inside the bucket: compare with the OTHER members only. The load is predicated (s-th member exists and
+            // is not this sample), so lanes whose bucket is exhausted put no traffic on the shared-memory pipe; an
+            // unloaded `o` stays NaN and compares false both ways.
+            const uint32_t tmp0 = (uint32_t)__cvta_generic_to_shared(sm.tmp);
+            for (int s = 0; s < M; ++s) {
+    #pragma unroll
+                for (int e = 0; e < EF; ++e) {
+                    float o = __uint_as_float(0x7fc00000u);
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.lt.s32 p, %2, %3;\n\t"
+                        "setp.ne.and.s32 p, %2, %4, p;\n\t"
+                        "@p ld.shared.f32 %0, [%1];\n\t}"
+                        : "+f"(o)
+                        : "r"(tmp0 + 4u * (uint32_t)(b[e] + s)), "r"(s), "r"(n[e]), "r"(slot[e])
+                        : "memory");
+                    r[e] += ((o < tf[e]) | ((o == tf[e]) & (s < slot[e]))) ? 1 : 0;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < EF; ++e) frank[e] = b[e] + r[e];
         }
         // ---- merged position = fine rank + #coarse below; bin idx holds exactly one coarse sample
 #pragma unroll
         for (int e = 0; e < EF; ++e) {
             const int below = idx[e] + (sm.tc[idx[e]] < tf[e] ? 1 : 0);
-            sm.out[b[e] + r[e] + below] = tf[e];
+            sm.out[frank[e] + below] = tf[e];
         }
         __syncwarp();
         // ---- coarse samples fill the empty slots in order; then verify
@@ -552,12 +594,15 @@ int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights, co
                            (uintptr_t)t_fine) & 15) == 0;
     if (aligned && ((Nc == 64 && Nf == 128) || (Nc == 128 && Nf == 256))) {
         unsigned g = (unsigned)((B + kSamplerWarps - 1) / kSamplerWarps);
-        if (Nc == 64)
-            sample_fine_fast_kernel<64, 128><<<g, kSamplerWarps * 32, 0, st>>>(B, bin_weights, bin_edges, t_coarse, u_fine,
-                                                                               seed, ray0, t_sorted, piece_idxs, cdf, t_fine);
-        else
-            sample_fine_fast_kernel<128, 256><<<g, kSamplerWarps * 32, 0, st>>>(B, bin_weights, bin_edges, t_coarse, u_fine,
-                                                                                seed, ray0, t_sorted, piece_idxs, cdf, t_fine);
+#define NB_LAUNCH_FAST(NCv, NFv, SRT)                                                                                   \
+    sample_fine_fast_kernel<NCv, NFv, SRT><<<g, kSamplerWarps * 32, 0, st>>>(B, bin_weights, bin_edges, t_coarse, u_fine, \
+                                                                             seed, ray0, t_sorted, piece_idxs, cdf, t_fine)
+        if (Nc == 64) {
+            if (u_fine) NB_LAUNCH_FAST(64, 128, false); else NB_LAUNCH_FAST(64, 128, true);
+        } else {
+            if (u_fine) NB_LAUNCH_FAST(128, 256, false); else NB_LAUNCH_FAST(128, 256, true);
+        }
+#undef NB_LAUNCH_FAST
         NB_LAUNCH_CHECK();
         return 0;
     }

@@ -316,3 +316,38 @@ def test_integrator_unaligned_and_short_batches():
             b = ru.post_process_model_output(rbuf[3:].view(B * S, 3), sbuf[1:], dev(t), True)
             for k in ("weights", "pred_rgb", "pred_depth", "acc_map"):
                 assert torch.equal(a[k], b[k]), (S, B, k)
+
+
+@pytest.mark.parametrize("Nc,Nf,B", [(64, 128, 8192), (128, 256, 4096)])
+def test_fine_sampler_in_kernel_uniforms_are_order_statistics(Nc, Nf, B):
+    """Without explicit uniforms the fast path draws the ORDER STATISTICS of Nf i.i.d. U[0,1) directly (normalised
+    partial sums of Nf+1 exponentials) instead of drawing Nf uniforms and sorting what they produce as the reference
+    does (ray_utils.py:355,385): same joint distribution. Checked on a uniform pdf over linear bins, where
+    t_fine = near + u * (far - near) up to rounding, against the Beta(k, Nf+1-k) moments of the k-th order statistic."""
+    near, far = F32(0.4), F32(1.2)
+    edges = rm.tf_linspace(np.full((B, 1), near, F32), np.full((B, 1), far, F32), Nc + 1)
+    tc = F32(0.5) * (edges[:, :-1] + edges[:, 1:])
+    w = np.ones((B, Nc), F32)
+    ts, dbg = ru.sample_fine(Nf, dev(w), dev(edges), dev(tc), None, seed=21, debug=True)
+    tf, idx = host(dbg["t_vals_fine"]).astype(np.float64), host(dbg["piece_idxs"])
+    u = (tf - near) / (far - near)
+    assert np.all(np.diff(u, axis=1) >= 0) and np.all(np.diff(idx, axis=1) >= 0)      # produced in order
+    assert u.min() >= -1e-6 and u.max() < 1 + 1e-5
+    assert np.array_equal(host(ts), np.sort(np.concatenate([tc, host(dbg["t_vals_fine"])], axis=1), axis=1))
+    k = np.arange(1, Nf + 1)
+    mean_k = k / (Nf + 1.0)
+    var_k = k * (Nf + 1.0 - k) / ((Nf + 1.0) ** 2 * (Nf + 2.0))
+    # mean of every order statistic: standard error sqrt(var_k / B) <= 5e-4; 6 sigma
+    assert np.abs(u.mean(0) - mean_k).max() <= 6 * np.sqrt(var_k.max() / B) + 2e-6
+    # variance of every order statistic within 12 % (relative s.e. of a variance estimate ~ sqrt(2/B) <= 2.2 %)
+    assert np.abs(u.var(0) / var_k - 1).max() <= 0.12
+    # a long gap U_(3Nf/4) - U_(Nf/4) is Beta(Nf/2, Nf/2+1): tests the joint law, not only the marginals
+    gap = u[:, 3 * Nf // 4 - 1] - u[:, Nf // 4 - 1]
+    a, b = Nf / 2.0, Nf / 2.0 + 1.0
+    assert abs(gap.mean() - a / (a + b)) <= 1e-3 and abs(gap.var() / (a * b / ((a + b) ** 2 * (a + b + 1))) - 1) <= 0.12
+    # pooled, the samples are uniform
+    assert abs(u.mean() - 0.5) <= 1e-3 and abs(u.var() - 1 / 12) <= 1e-3
+    # different rays and different seeds give different draws; the same seed repeats
+    assert not np.array_equal(u[0], u[1])
+    ts2 = ru.sample_fine(Nf, dev(w), dev(edges), dev(tc), None, seed=22)
+    assert not torch.equal(ts2, ts) and torch.equal(ru.sample_fine(Nf, dev(w), dev(edges), dev(tc), None, seed=21), ts)
