@@ -149,6 +149,91 @@ class KernelTimer:
         return {n: (sum(e0.elapsed_time(e1) for e0, e1 in evs), len(evs)) for n, evs in self.ev.items()}
 
 
+def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_FINE):
+    """The HBM-bound kernels of the path timed ALONE at the render chunk size: back-to-back launches through the C ABI
+    with preallocated outputs, CUDA events around the batch, inputs rotated through sets that together exceed 2x L2.
+    (Event brackets around single launches inside a render step add several microseconds of launch gap to kernels
+    that run for 15-50 us, so the in-step figures understate them.) Returns one dict per kernel: algorithmic bytes
+    per ray, microseconds per launch, GB/s."""
+    import torch
+    from nerf_tf2_b200 import ray_utils as ru
+    from nerf_tf2_b200._lib import load, ptr, stream_ptr, check
+
+    B, Nc, Nf, S = rays, nc, nf, nc + nf
+    g = torch.Generator(device="cuda").manual_seed(0)
+    L2 = 126e6
+    lib, st = load(), stream_ptr()
+    results = []
+
+    def nsets(bytes_per_set):
+        return sets if sets else max(2, int(2 * L2 / bytes_per_set) + 1)
+
+    def timed(fn, data):
+        for i in range(warmup):
+            fn(data[i % len(data)])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(data[i % len(data)])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def rnd(*shape):
+        return torch.rand(shape, device="cuda", generator=g)
+
+    def sigma_like(n):       # sigma == 0 for most samples, like a random-init network (SURVEY.md App. E)
+        return rnd(n) * 20 * (rnd(n) > 0.6)
+
+    for key, name, s, need_w in (("composite_coarse", "composite_fwd_kernel<2,full> (coarse, weights out)", Nc, True),
+                                 ("composite_fine", "composite_fwd_kernel<6,full> (fine, render: no weights)", S, False),
+                                 ("composite_fine_w", "composite_fwd_kernel<6,full> (fine, weights out)", S, True)):
+        bpr = (24 if need_w else 20) * s + 20
+        data = [(rnd(B * s, 3), sigma_like(B * s), torch.sort(rnd(B, s) * 0.8 + 0.4, dim=1).values.contiguous())
+                for _ in range(nsets(B * bpr))]
+        wts = torch.empty((B, s), device="cuda") if need_w else None
+        prgb, pdep, pacc = torch.empty((B, 3), device="cuda"), torch.empty((B,), device="cuda"), torch.empty((B,), device="cuda")
+
+        def run(x):
+            check(lib.nerfb200_composite_fwd(B, s, ptr(x[1]), ptr(x[0]), ptr(x[2]), 1, ptr(wts, allow_none=True), ptr(prgb),
+                                             ptr(pdep), ptr(pacc), st), "composite_fwd")
+        ms = timed(run, data)
+        results.append({"key": key, "kernel": name, "rays": B, "S": s, "bytes_per_ray": bpr, "us": ms * 1e3,
+                        "GBps": B * bpr / (ms / 1e3) / 1e9, "input_sets": len(data)})
+        del data
+
+    near, far = torch.full((B,), 0.425, device="cuda"), torch.full((B,), 1.275, device="cuda")
+    for key, name, with_u in (("sample_fine", f"sample_fine_fast_kernel<{Nc},{Nf},sorted> (in-kernel uniforms)", False),
+                              ("sample_fine_u", f"sample_fine_fast_kernel<{Nc},{Nf}> (explicit uniforms)", True)):
+        # weights + bin edges + t_coarse read, t_sorted written (+ u read)
+        bpr = 4 * Nc * 2 + 4 * (Nc + 1) + 4 * S + (4 * Nf if with_u else 0)
+        data = []
+        for i in range(nsets(B * bpr)):
+            t_c, edges = ru.sample_coarse(Nc, True, True, near, far, None, seed=i, ray0=0)
+            data.append((ru.compute_weights(sigma_like(B * Nc), t_c), edges, t_c, rnd(B, Nf) if with_u else None))
+        tso = torch.empty((B, S), device="cuda")
+
+        def run(x):
+            check(lib.nerfb200_sample_fine(B, Nc, Nf, ptr(x[0]), ptr(x[1]), ptr(x[2]), ptr(x[3], allow_none=True), 1, 0,
+                                           ptr(tso), None, None, None, st), "sample_fine")
+        ms = timed(run, data)
+        results.append({"key": key, "kernel": name, "rays": B, "Nc": Nc, "Nf": Nf, "bytes_per_ray": bpr, "us": ms * 1e3,
+                        "GBps": B * bpr / (ms / 1e3) / 1e9, "input_sets": len(data)})
+        del data
+
+    # stratified sampler: near/far read, t and the bin edges written, uniforms generated in-kernel
+    bpr = 8 + 4 * Nc + 4 * (Nc + 1)
+    outs = [(torch.empty((B, Nc), device="cuda"), torch.empty((B, Nc + 1), device="cuda")) for _ in range(nsets(B * bpr))]
+
+    def run(x):
+        check(lib.nerfb200_sample_coarse(B, Nc, 1, 1, ptr(near), ptr(far), None, 1, 0, ptr(x[0]), ptr(x[1]), st), "sample_coarse")
+    ms = timed(run, outs)
+    results.append({"key": "sample_coarse", "kernel": "sample_coarse_kernel (in-kernel uniforms, 1/t spacing)", "rays": B, "Nc": Nc,
+                    "bytes_per_ray": bpr, "us": ms * 1e3, "GBps": B * bpr / (ms / 1e3) / 1e9, "input_sets": len(outs)})
+    return results
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -235,6 +320,9 @@ def run_b200(args):
     sf_ms, sf_n = tot["sample_fine"]
     # weights 4Nc + bin edges 4(Nc+1) + t_coarse 4Nc read, t_sorted 4(Nc+Nf) written; u generated in-kernel
     sf_bytes = args.steps * n_rays * (4 * N_COARSE * 2 + 4 * (N_COARSE + 1) + 4 * (N_COARSE + N_FINE))
+    sc_ms, sc_n = tot["sample_coarse"]
+    # near/far read, t [B,Nc] and bin edges [B,Nc+1] written; u generated in-kernel
+    sc_bytes = args.steps * n_rays * (8 + 4 * N_COARSE + 4 * (N_COARSE + 1))
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -245,13 +333,29 @@ def run_b200(args):
                 "peak_kind": f"bf16 sustained, {pk['source']}", "frac_of_burst": mlp_tflops / pk["tensor_burst"],
                 "traffic": traffic, "launches": mlp_n, "avg_launch_ms": mlp_ms / mlp_n,
                 "share_of_step": mlp_ms / ms_b, "traffic_note": traffic_note}
+    in_step = {"composite": comp_bytes / (comp_ms / 1e3) / 1e9, "sample_fine": sf_bytes / (sf_ms / 1e3) / 1e9,
+               "sample_coarse": sc_bytes / (sc_ms / 1e3) / 1e9}
+    alone = {r["key"]: r for r in hbm_kernels_alone(rays=args.chunk)}
+    # the integrator as the render uses it: one coarse launch (weights out) + one fine launch (no weights) per chunk
+    ca, cf = alone["composite_coarse"], alone["composite_fine"]
+    comp_alone = (ca["bytes_per_ray"] + cf["bytes_per_ray"]) * ca["rays"] / ((ca["us"] + cf["us"]) * 1e-6) / 1e9
+    how = ("achieved: back-to-back launches of the kernel alone at the render chunk size, CUDA events around the batch, inputs "
+           "rotated through sets > 2x L2; in_step_GBps: CUDA-event brackets around each single launch inside the render step "
+           "(includes the launch gaps, which are comparable to a 15-50 us kernel)")
     roofline_hbm = [
-        {"kernel": "composite_fwd_kernel<2,full> + <6,full> (coarse with weights, fine without)", "bound": "hbm", "achieved": comp_bytes / (comp_ms / 1e3) / 1e9, "peak": pk["hbm"],
-         "unit": "GB/s", "frac": comp_bytes / (comp_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": comp_n,
-         "share_of_step": comp_ms / ms_b},
-        {"kernel": "sample_fine_fast_kernel<64,128>", "bound": "hbm", "achieved": sf_bytes / (sf_ms / 1e3) / 1e9, "peak": pk["hbm"],
-         "unit": "GB/s", "frac": sf_bytes / (sf_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launches": sf_n,
-         "share_of_step": sf_ms / ms_b},
+        {"kernel": "composite_fwd_kernel<2,full> + <6,full> (coarse with weights, fine without)", "bound": "hbm",
+         "achieved": comp_alone, "peak": pk["hbm"], "unit": "GB/s", "frac": comp_alone / pk["hbm"], "traffic": None,
+         "us_per_launch": [ca["us"], cf["us"]], "frac_coarse": ca["GBps"] / pk["hbm"], "frac_fine": cf["GBps"] / pk["hbm"],
+         "in_step_GBps": in_step["composite"], "launches": comp_n, "share_of_step": comp_ms / ms_b, "timing": how},
+        {"kernel": alone["sample_fine"]["kernel"], "bound": "hbm", "achieved": alone["sample_fine"]["GBps"], "peak": pk["hbm"],
+         "unit": "GB/s", "frac": alone["sample_fine"]["GBps"] / pk["hbm"], "traffic": None,
+         "us_per_launch": alone["sample_fine"]["us"], "in_step_GBps": in_step["sample_fine"], "launches": sf_n,
+         "share_of_step": sf_ms / ms_b,
+         "note": "instruction-issue bound (about 600 warp instructions per ray), not HBM bound: DESIGN.md section 4.4"},
+        {"kernel": alone["sample_coarse"]["kernel"], "bound": "hbm", "achieved": alone["sample_coarse"]["GBps"], "peak": pk["hbm"],
+         "unit": "GB/s", "frac": alone["sample_coarse"]["GBps"] / pk["hbm"], "traffic": None,
+         "us_per_launch": alone["sample_coarse"]["us"], "in_step_GBps": in_step["sample_coarse"], "launches": sc_n,
+         "share_of_step": sc_ms / ms_b},
     ]
 
     # ---- timed region 2: end to end through NeRF.predict() with HOST rays (pinned), H2D + D2H included

@@ -101,32 +101,57 @@ __device__ __forceinline__ float bin_edge(float near, float far, int k, int Nc, 
     return __fdiv_rn(1.0f, v);
 }
 
+// One thread per (ray, group of 4 consecutive bins): the ray's reciprocals and the linspace delta are computed once
+// per group instead of once per edge, the 5 edges of the group are shared by its 4 samples, and ONE Philox call
+// yields the 4 uniforms (counter block = k >> 2, as everywhere). Every value is produced by exactly the operations of
+// bin_edge() above, in the same order: bit-identical to the one-thread-per-edge form.
 __global__ void sample_coarse_kernel(int64_t B, int Nc, int lin_inv, int perturb, const float* __restrict__ near,
                                      const float* __restrict__ far, const float* __restrict__ u_in, uint64_t seed,
                                      int64_t ray0, float* __restrict__ t_vals, float* __restrict__ edges) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = B * (Nc + 1);
-    if (i >= total) return;
-    int64_t ray = i / (Nc + 1);
-    int k = (int)(i - ray * (Nc + 1));
-    float n = near[ray], f = far[ray];
-    float left = bin_edge(n, f, k, Nc, lin_inv);
-    edges[i] = left;
-    if (k == Nc) return;
-    float right = bin_edge(n, f, k + 1, Nc, lin_inv);
-    float t;
-    if (perturb) {
-        float u;
-        if (u_in) u = u_in[ray * Nc + k];
-        else {
-            float4 r = philox_uniform4(seed, (uint64_t)(ray0 + ray), (uint32_t)(k >> 2), 0u);
-            u = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
-        }
-        t = __fadd_rn(left, __fmul_rn(u, __fsub_rn(right, left)));       // utils/ray_utils.py:234
-    } else {
-        t = __fmul_rn(0.5f, __fadd_rn(left, right));                      // utils/ray_utils.py:243
+    const int G = (Nc + 3) >> 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * G) return;
+    const int64_t ray = i / G;
+    const int k0 = 4 * (int)(i - ray * G);
+    const float n = near[ray], f = far[ray];
+    const float a = lin_inv ? __fdiv_rn(1.0f, n) : n, b = lin_inv ? __fdiv_rn(1.0f, f) : f;
+    const float delta = __fdiv_rn(__fsub_rn(b, a), (float)Nc);
+    float e[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int k = k0 + j;
+        float v = (k == 0) ? a : ((k >= Nc) ? b : __fadd_rn(a, __fmul_rn(delta, (float)k)));
+        e[j] = lin_inv ? __fdiv_rn(1.0f, v) : v;
     }
-    t_vals[ray * Nc + k] = t;
+    float* erow = edges + ray * (Nc + 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (k0 + j <= Nc) erow[k0 + j] = e[j];
+    if (k0 + 4 == Nc) erow[Nc] = e[4];
+    float u[4] = {0.f, 0.f, 0.f, 0.f};
+    if (perturb) {
+        if (u_in) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k0 + j < Nc) u[j] = u_in[ray * Nc + k0 + j];
+        } else {
+            const float4 r = philox_uniform4(seed, (uint64_t)(ray0 + ray), (uint32_t)(k0 >> 2), 0u);
+            u[0] = r.x; u[1] = r.y; u[2] = r.z; u[3] = r.w;
+        }
+    }
+    float t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        t[j] = perturb ? __fadd_rn(e[j], __fmul_rn(u[j], __fsub_rn(e[j + 1], e[j])))     // utils/ray_utils.py:234
+                       : __fmul_rn(0.5f, __fadd_rn(e[j], e[j + 1]));                      // utils/ray_utils.py:243
+    float* trow = t_vals + ray * Nc + k0;
+    if ((Nc & 3) == 0 && (((uintptr_t)t_vals) & 15) == 0) {
+        *reinterpret_cast<float4*>(trow) = make_float4(t[0], t[1], t[2], t[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (k0 + j < Nc) trow[j] = t[j];
+    }
 }
 
 // xyz = o + t*d, dirs broadcast (utils/ray_utils.py:251-258). One thread per row.
@@ -287,7 +312,7 @@ int nerfb200_sample_coarse(int64_t B, int Nc, int lin_inv_depth, int perturb, co
     NB_CHECK_ARG(B >= 0 && Nc >= 2, "sample_coarse: bad shape");
     if (B == 0) return 0;
     NB_CHECK_ARG(near && far && t_vals && bin_edges, "sample_coarse: NULL pointer");
-    sample_coarse_kernel<<<blocks_for(B * (Nc + 1), 256), 256, 0, (cudaStream_t)stream>>>(
+    sample_coarse_kernel<<<blocks_for(B * ((Nc + 3) / 4), 256), 256, 0, (cudaStream_t)stream>>>(
         B, Nc, lin_inv_depth, perturb, near, far, u_coarse, seed, ray0, t_vals, bin_edges);
     NB_LAUNCH_CHECK();
     return 0;

@@ -191,6 +191,10 @@ def test_bench_line_contract():
     e = d["e2e"]
     assert e["value"] > 1e5 and e["h2d_bytes_per_step"] == 640000 * 8 * 4 and e["d2h_bytes_per_step"] == 640000 * 10 * 4
     assert "sm_mhz" in d["clocks"] and "reasons" in d["clocks"] and "workload" in d["config"]
+    # the HBM-bound kernels, timed alone against the measured copy bandwidth
+    hb = d["roofline_hbm"]
+    assert len(hb) == 3 and all(h["bound"] == "hbm" and 0 < h["frac"] < 1.2 and h["in_step_GBps"] > 0 for h in hb)
+    assert all(abs(h["frac"] - h["achieved"] / h["peak"]) < 1e-9 for h in hb)
 
 
 def test_render_spherical_path_script_loop(tmp_path):

@@ -351,3 +351,21 @@ def test_fine_sampler_in_kernel_uniforms_are_order_statistics(Nc, Nf, B):
     assert not np.array_equal(u[0], u[1])
     ts2 = ru.sample_fine(Nf, dev(w), dev(edges), dev(tc), None, seed=22)
     assert not torch.equal(ts2, ts) and torch.equal(ru.sample_fine(Nf, dev(w), dev(edges), dev(tc), None, seed=21), ts)
+
+
+@pytest.mark.parametrize("Nc", [2, 7, 10, 64, 130])
+@pytest.mark.parametrize("lin_inv", [True, False])
+def test_coarse_sampler_any_bin_count_bit_exact(Nc, lin_inv):
+    """The stratified sampler works on groups of 4 bins per thread; bin counts that are not multiples of 4, with
+    and without perturbation, must still be bit-identical to the oracle."""
+    rng = np.random.default_rng(100 + Nc)
+    B = 53
+    near = (rng.random((B, 1), dtype=F32) * F32(0.3) + F32(0.3)).astype(F32)
+    far = (near + F32(0.5) + rng.random((B, 1), dtype=F32)).astype(F32)
+    u = rng.random((B, Nc), dtype=F32)
+    z = np.zeros((B, 3), F32)
+    for perturb, uu in ((True, u), (False, None)):
+        o = rm.create_input_batch_coarse_model(Nc, lin_inv, perturb, z, z + 1, near, far, uu)
+        t, e = ru.sample_coarse(Nc, lin_inv, perturb, dev(near), dev(far), None if uu is None else dev(uu))
+        assert np.array_equal(host(e), o["bin_data"]["bin_edges"])
+        assert np.array_equal(host(t), o["t_vals"])
