@@ -148,9 +148,16 @@ NERFB200_API int nerfb200_composite_bwd(int64_t B, int S, const float* sigma, co
 /* ---- a10: hierarchical (inverse-transform) sampler ----------------------------------------
  * create_input_batch_fine_model (utils/ray_utils.py:276-406): pdf/cdf from (w+1e-5), upper-bound
  * searchsorted over the Nc-1 inner CDF edges, inversion with the pdf<1e-8 mask, then
- * sort(concat(t_coarse, t_fine)). u = u_fine[B,Nf] if non-NULL else Philox(seed, ray0+ray, j).
+ * sort(concat(t_coarse, t_fine)). u = u_fine[B,Nf] if non-NULL (reproduces a given
+ * tf.random.uniform draw: searchsorted indices bit-exact on the kernel's fp32 CDF, output the
+ * exact ascending sort). With u_fine NULL the uniforms come from Philox(seed, ray0+ray): the
+ * 64/128 and 128/256 shapes draw the ORDER STATISTICS of Nf i.i.d. U[0,1) directly (normalised
+ * partial sums of Nf+1 exponentials - the same joint distribution as drawing Nf uniforms and
+ * sorting, which is what the reference does at :355,:385), other shapes draw u_j i.i.d.; both
+ * are pure functions of (seed, global ray id), hence independent of sharding and chunking.
  * Optional debug outputs (NULL to skip): piece_idxs[B,Nf] int32, cdf[B,Nc+1] (the fp32 CDF the
- * indices were searched in), t_fine[B,Nf] unsorted. Nc in {32..256 step 32}, Nf multiple of 32. */
+ * indices were searched in), t_fine[B,Nf] in the order of u. Nc in {32..256 step 32}, Nf in
+ * {32,64,128,256,512}. */
 NERFB200_API int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights,
                          const float* bin_edges, const float* t_coarse, const float* u_fine,
                          uint64_t seed, int64_t ray0, float* t_sorted /* [B,Nc+Nf] */,

@@ -82,7 +82,7 @@ def test_integrator_matches_reference_fixture(golden, tag):
     assert np.allclose(host(w), g[f"{tag}_wb0_weights"], rtol=2e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("S", [2, 33, 64, 100, 192, 384, 512, 1000])
+@pytest.mark.parametrize("S", [2, 32, 33, 64, 96, 100, 128, 192, 256, 384, 512, 1000, 1024])
 def test_integrator_ragged_sample_counts(S):
     rng = np.random.default_rng(S)
     B = 37
