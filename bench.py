@@ -342,13 +342,16 @@ def run_b200(args):
     how = ("achieved: back-to-back launches of the kernel alone at the render chunk size, CUDA events around the batch, inputs "
            "rotated through sets > 2x L2; in_step_GBps: CUDA-event brackets around each single launch inside the render step "
            "(includes the launch gaps, which are comparable to a 15-50 us kernel)")
+    tk = (tj.get("hbm_kernels_dram_bytes_per_launch") if os.path.exists(tpath) else None) or {}
     roofline_hbm = [
         {"kernel": "composite_fwd_kernel<2,full> + <6,full> (coarse with weights, fine without)", "bound": "hbm",
-         "achieved": comp_alone, "peak": pk["hbm"], "unit": "GB/s", "frac": comp_alone / pk["hbm"], "traffic": None,
+         "achieved": comp_alone, "peak": pk["hbm"], "unit": "GB/s", "frac": comp_alone / pk["hbm"],
+         "traffic": [tk.get("composite_coarse"), tk.get("composite_fine")] if tk else None,
          "us_per_launch": [ca["us"], cf["us"]], "frac_coarse": ca["GBps"] / pk["hbm"], "frac_fine": cf["GBps"] / pk["hbm"],
          "in_step_GBps": in_step["composite"], "launches": comp_n, "share_of_step": comp_ms / ms_b, "timing": how},
         {"kernel": alone["sample_fine"]["kernel"], "bound": "hbm", "achieved": alone["sample_fine"]["GBps"], "peak": pk["hbm"],
-         "unit": "GB/s", "frac": alone["sample_fine"]["GBps"] / pk["hbm"], "traffic": None,
+         "unit": "GB/s", "frac": alone["sample_fine"]["GBps"] / pk["hbm"], "traffic": tk.get("sample_fine"),
+         "traffic_note": tk.get("note"),
          "us_per_launch": alone["sample_fine"]["us"], "in_step_GBps": in_step["sample_fine"], "launches": sf_n,
          "share_of_step": sf_ms / ms_b,
          "note": "instruction-issue bound (about 600 warp instructions per ray), not HBM bound: DESIGN.md section 4.4"},

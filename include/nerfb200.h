@@ -130,6 +130,16 @@ NERFB200_API int nerfb200_mlp_backward(nerfb200_ctx* ctx, int which, int64_t B, 
                           const float* rays_d, const float* t_vals, const float* flat_params,
                           const float* d_rgb, const float* d_sigma, float* flat_grads,
                           int precision, void* workspace, void* stash, void* stream);
+/* The same backward pass as two separately launchable phases (tensor-core precisions only; FP32 returns
+ * NERFB200_ENOTSUP): _data writes the per-layer gradient stash into `workspace` (HBM-write bound), _weights
+ * reads both stashes and accumulates into flat_grads (HBM-read bound). max_sms > 0 caps the SMs a phase
+ * occupies (0 = all), so a caller can run one model's _weights next to the other model's _data on disjoint
+ * SMs and two streams; each model then needs its own workspace. mlp_backward == _data then _weights, max_sms 0. */
+NERFB200_API int nerfb200_mlp_backward_data(nerfb200_ctx* ctx, int which, int64_t B, int S, const float* flat_params,
+                               const float* d_rgb, const float* d_sigma, int precision, void* workspace,
+                               void* stash, int max_sms, void* stream);
+NERFB200_API int nerfb200_mlp_backward_weights(nerfb200_ctx* ctx, int which, int64_t B, int S, float* flat_grads,
+                                  int precision, void* workspace, void* stash, int max_sms, void* stream);
 
 /* ---- a7-a9: volume-rendering integrator --------------------------------------------------
  * sigma_to_alpha / compute_weights / post_process_model_output (utils/ray_utils.py:408-551):

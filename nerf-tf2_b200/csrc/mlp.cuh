@@ -39,5 +39,9 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
 int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd,
                 const float* t, const float* flat_params, const float* d_rgb, const float* d_sigma, float* flat_grads,
                 void* workspace, void* stash, cudaStream_t st);
+int tc_backward_data(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* flat_params, const float* d_rgb,
+                     const float* d_sigma, void* workspace, void* stash, int max_sms, cudaStream_t st);
+int tc_backward_weights(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, float* flat_grads, void* workspace,
+                        void* stash, int max_sms, cudaStream_t st);
 
 }  // namespace nb

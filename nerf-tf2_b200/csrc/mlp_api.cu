@@ -76,4 +76,32 @@ int nerfb200_mlp_backward(nerfb200_ctx* ctx, int which, int64_t B, int S, const 
                        flat_grads, workspace, stash, st);
 }
 
+int nerfb200_mlp_backward_data(nerfb200_ctx* ctx, int which, int64_t B, int S, const float* flat_params, const float* d_rgb,
+                               const float* d_sigma, int precision, void* workspace, void* stash, int max_sms, void* stream) {
+    int rc = check_common("mlp_backward_data", ctx, which, B, S, precision);
+    if (rc) return rc;
+    if (precision == NERFB200_FP32) {
+        set_error("mlp_backward_data: the phase-split backward exists for the tensor-core precisions only");
+        return NERFB200_ENOTSUP;
+    }
+    NB_CHECK_ARG(flat_params && d_rgb && d_sigma && max_sms >= 0, "mlp_backward_data: bad argument");
+    if (B == 0) return 0;
+    return tc_backward_data(ctx, which, precision == NERFB200_FP16, B, S, flat_params, d_rgb, d_sigma, workspace, stash, max_sms,
+                            (cudaStream_t)stream);
+}
+
+int nerfb200_mlp_backward_weights(nerfb200_ctx* ctx, int which, int64_t B, int S, float* flat_grads, int precision,
+                                  void* workspace, void* stash, int max_sms, void* stream) {
+    int rc = check_common("mlp_backward_weights", ctx, which, B, S, precision);
+    if (rc) return rc;
+    if (precision == NERFB200_FP32) {
+        set_error("mlp_backward_weights: the phase-split backward exists for the tensor-core precisions only");
+        return NERFB200_ENOTSUP;
+    }
+    NB_CHECK_ARG(flat_grads && max_sms >= 0, "mlp_backward_weights: bad argument");
+    if (B == 0) return 0;
+    return tc_backward_weights(ctx, which, precision == NERFB200_FP16, B, S, flat_grads, workspace, stash, max_sms,
+                               (cudaStream_t)stream);
+}
+
 }  // extern "C"

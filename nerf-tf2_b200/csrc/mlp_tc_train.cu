@@ -905,20 +905,21 @@ static void plan_dw(const DwJob* jobs, int grid, DwParams& dp, ReduceParams& rp)
     }
 }
 
-int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
-                const float* flat_params, const float* d_rgb, const float* d_sigma, float* flat_grads, void* workspace, void* stash,
-                cudaStream_t st) {
-    (void)ro; (void)rd; (void)t;
+// The backward pass of one model is two phases with different HBM behaviour: backward-data WRITES the gradient stash
+// (write bound), the weight-gradient GEMM READS both stashes (read bound). `max_sms` > 0 caps the SMs a phase may
+// occupy (both kernels are persistent, one CTA per SM), so that the caller can run the coarse model's weight-gradient
+// phase next to the fine model's backward-data phase on disjoint SMs and keep reads and writes in flight together.
+int tc_backward_data(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* flat_params, const float* d_rgb,
+                     const float* d_sigma, void* workspace, void* stash, int max_sms, cudaStream_t st) {
     if (!ctx->packed_valid) { set_error("mlp_backward: pack_weights has not been called"); return NERFB200_ESTATE; }
     NB_CHECK_ARG(workspace && stash, "mlp_backward: workspace and stash required");
     const int64_t R = B * S;
     if (R == 0) return 0;
     const int num_tiles = (int)tiles_of(R);
-    const int sms = ctx->num_sms;
+    int sms = ctx->num_sms;
+    if (max_sms > 0 && max_sms < sms) sms = max_sms < 2 ? 2 : max_sms;
     uint8_t* gstash = (uint8_t*)workspace;
-    float* partial0 = (float*)(gstash + (size_t)num_tiles * kGradTileBytes);
     const float* P = flat_params + (int64_t)which * kParamsPerModel;
-    float* G = flat_grads + (int64_t)which * kParamsPerModel;
 
     BwdParams bp;
     bp.wimg = (const uint8_t*)ctx->packed_bwd[half ? 1 : 0][which];
@@ -935,20 +936,57 @@ int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const 
     } else if (half) bwd_data_kernel<true><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
     else bwd_data_kernel<false><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
     NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int tc_backward_weights(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, float* flat_grads, void* workspace,
+                        void* stash, int max_sms, cudaStream_t st) {
+    NB_CHECK_ARG(workspace && stash, "mlp_backward: workspace and stash required");
+    const int64_t R = B * S;
+    if (R == 0) return 0;
+    const int num_tiles = (int)tiles_of(R);
+    int sms = ctx->num_sms;
+    if (max_sms > 0 && max_sms < sms) sms = max_sms;
+    uint8_t* gstash = (uint8_t*)workspace;
+    float* partial0 = (float*)(gstash + (size_t)num_tiles * kGradTileBytes);
+    float* G = flat_grads + (int64_t)which * kParamsPerModel;
 
     DwJob jobs[kDwJobs];
     build_dw_jobs(jobs);
-    const int dgrid = sms > kDwJobs ? sms : kDwJobs;
+    int dgrid = sms > kDwJobs ? sms : kDwJobs;
+    const bool capped = max_sms > 0 && max_sms < ctx->num_sms;
+    if (capped) dgrid &= ~1;
     DwParams dp;
     ReduceParams rp;
     plan_dw(jobs, dgrid, dp, rp);
     dp.stash = (const uint8_t*)stash; dp.gstash = gstash; dp.partial = partial0; dp.num_tiles = num_tiles;
-    if (half) dw_kernel<true><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
+    if (capped) {
+        // launched as 2-CTA clusters (the kernel itself does not use the cluster): a pair lands on the two SMs of one
+        // TPC, so the SMs this phase leaves free are whole TPCs, which is what the cta_group::2 pairs of the
+        // backward-data kernel running next to it need
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)dgrid); cfg.blockDim = dim3(kDwThreads); cfg.dynamicSmemBytes = kDwSmemTotal; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (half) NB_CUDA(cudaLaunchKernelEx(&cfg, dw_kernel<true>, dp));
+        else NB_CUDA(cudaLaunchKernelEx(&cfg, dw_kernel<false>, dp));
+    } else if (half) dw_kernel<true><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
     else dw_kernel<false><<<dgrid, kDwThreads, kDwSmemTotal, st>>>(dp);
     NB_LAUNCH_CHECK();
     reduce_grads_kernel<<<dim3((256 * 256 + 256 + 255) / 256, kDwJobs), 256, 0, st>>>(rp, partial0, G);
     NB_LAUNCH_CHECK();
     return 0;
+}
+
+int tc_backward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
+                const float* flat_params, const float* d_rgb, const float* d_sigma, float* flat_grads, void* workspace, void* stash,
+                cudaStream_t st) {
+    (void)ro; (void)rd; (void)t;
+    int rc = tc_backward_data(ctx, which, half, B, S, flat_params, d_rgb, d_sigma, workspace, stash, 0, st);
+    if (rc) return rc;
+    return tc_backward_weights(ctx, which, half, B, S, flat_grads, workspace, stash, 0, st);
 }
 
 }  // namespace nb

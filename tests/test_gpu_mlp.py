@@ -208,3 +208,26 @@ def test_tensor_core_training_reduces_loss():
     nerf.fit(x=ds, epochs=2, steps_per_epoch=16)
     after = nerf.evaluate(val)
     assert after > before + 1.0, (before, after)
+
+
+@pytest.mark.parametrize("n_dw", [14, 48, 100])
+def test_overlapped_backward_equals_sequential_backward(golden, n_dw):
+    """The phase-split backward (coarse weight-gradient phase on `n_dw` SMs and a second stream, next to the fine
+    backward-data phase on the rest) computes the same gradients as the sequential one. Same kernels, same operands;
+    only the K-split of the weight-gradient GEMM (hence the fp32 summation order) depends on the SM count."""
+    g = golden["oracle_forward_train"]
+    dv = lambda k: dev(g[k])
+    args = (dv("rays_o"), dv("rays_d"), dv("near"), dv("far"), dv("rgb_gt"))
+    grads = []
+    for n in (0, n_dw):
+        nerf = make_nerf(om.init_weights(7), "bf16", train_precision="bf16")
+        nerf._dw_overlap_sms = n
+        for _ in range(2):                                  # twice: the second pass reuses stashes, streams, workspaces
+            loss, _, _ = nerf._loss_and_grads(*args, u_fine=dv("u_fine"))
+        torch.cuda.synchronize()
+        grads.append((float(loss.item()), nerf.flat_grads.double().clone()))
+    (l0, a), (l1, b) = grads
+    assert l0 == l1
+    scale = float(a.abs().max())
+    assert float((a - b).abs().max()) <= 2e-5 * scale
+    assert float(torch.nn.functional.cosine_similarity(a, b, dim=0)) >= 1 - 1e-9
