@@ -423,7 +423,7 @@ class NeRF:
         self.optimizer.apply_gradients(self.flat_grads)
         self._step_counter += 1
         self.last_loss = loss
-        return {m.name: m.result() for m in self.metrics}
+        return {m.name: m.result_async() for m in self.metrics}     # no device sync: see PSNRMetric.result_async
 
     def test_step(self, data, u_coarse=None, u_fine=None):
         """NeRF.test_step (core/model.py:182-223): forward + metric update on the fine output."""
@@ -432,7 +432,7 @@ class NeRF:
         _, pp_f = self.forward(ro, rd, near, far, u_coarse, u_fine, need_weights=False)
         for m in self.metrics:
             m.update_state(rgb, pp_f["pred_rgb"])
-        return {m.name: m.result() for m in self.metrics}
+        return {m.name: m.result_async() for m in self.metrics}
 
     def predict_step(self, data):
         """NeRF.predict_step (core/model.py:225-237)."""

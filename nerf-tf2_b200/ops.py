@@ -13,6 +13,45 @@ import numpy as np
 import torch
 
 
+class MetricValue:
+    """A PSNRMetric result that stays on the device until it is used as a number (float(), formatting, comparisons,
+    arithmetic, NumPy conversion all work and synchronise once)."""
+    __slots__ = ("_snap", "_val")
+
+    def __init__(self, snapshot):
+        self._snap, self._val = snapshot, None
+
+    def _get(self):
+        if self._val is None:
+            sq, cnt = self._snap.tolist()
+            self._val, self._snap = PSNRMetric._psnr(sq, cnt), None
+        return self._val
+
+    def __float__(self): return self._get()
+    def __array__(self, dtype=None, copy=None): return np.asarray(self._get(), dtype=dtype)
+    def __repr__(self): return repr(self._get())
+    def __str__(self): return str(self._get())
+    def __format__(self, spec): return format(self._get(), spec)
+    def __bool__(self): return bool(self._get())
+    def __hash__(self): return hash(self._get())
+    def __eq__(self, o): return self._get() == float(o)
+    def __lt__(self, o): return self._get() < float(o)
+    def __le__(self, o): return self._get() <= float(o)
+    def __gt__(self, o): return self._get() > float(o)
+    def __ge__(self, o): return self._get() >= float(o)
+    def __neg__(self): return -self._get()
+    def __abs__(self): return abs(self._get())
+    def __round__(self, n=None): return round(self._get(), n)
+    def __add__(self, o): return self._get() + float(o)
+    def __radd__(self, o): return float(o) + self._get()
+    def __sub__(self, o): return self._get() - float(o)
+    def __rsub__(self, o): return float(o) - self._get()
+    def __mul__(self, o): return self._get() * float(o)
+    def __rmul__(self, o): return float(o) * self._get()
+    def __truediv__(self, o): return self._get() / float(o)
+    def __rtruediv__(self, o): return float(o) / self._get()
+
+
 class PSNRMetric:
     """ops.PSNRMetric (core/ops.py:187-238)."""
 
@@ -30,13 +69,26 @@ class PSNRMetric:
         self.state[0] += torch.sum(torch.square(y_true - y_pred))
         self.state[1] += float(y_true.shape[0])
 
+    @staticmethod
+    def _psnr(sq, cnt):
+        if cnt == 0 or sq <= 0:
+            return float("inf") if cnt else float("nan")
+        return -10.0 * (math.log(sq / cnt) / math.log(10.0))
+
     def result(self):
         if self.state is None:
             return float("nan")
         sq, cnt = self.state.tolist()
-        if cnt == 0 or sq <= 0:
-            return float("inf") if cnt else float("nan")
-        return -10.0 * (math.log(sq / cnt) / math.log(10.0))
+        return self._psnr(sq, cnt)
+
+    def result_async(self):
+        """The metric value as of now WITHOUT synchronising with the device: a tiny device-side snapshot of the state,
+        turned into a Python float only when somebody looks at it. train_step / test_step return these (Keras hands
+        back tensors from its step functions for the same reason): a training loop that does not read the per-step
+        logs never stalls the launch queue."""
+        if self.state is None:
+            return float("nan")
+        return MetricValue(self.state.clone())
 
     def reset_states(self):
         if self.state is not None:

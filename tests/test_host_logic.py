@@ -1,5 +1,6 @@
 """CPU: host-side logic of the package (dataset batching, params, PSNR, init, scene)."""
 import numpy as np
+import pytest
 import torch
 
 import nerf_tf2_b200 as nb
@@ -99,3 +100,19 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_metric_value_is_a_lazy_number():
+    """train_step / test_step hand back PSNRMetric.result_async(): a snapshot that turns into a float on first use."""
+    import json
+    import torch
+    m = nb.PSNRMetric()
+    y = torch.rand(16, 3); p = torch.rand(16, 3)
+    m.update_state(y, p)
+    v, ref = m.result_async(), m.result()
+    m.update_state(y, p * 0.5)                      # later updates do not change the snapshot
+    assert float(v) == ref and abs(v - ref) == 0 and v == ref and not (v < ref) and v >= ref
+    assert np.isfinite(v) and f"{v:.3f}" == f"{ref:.3f}" and repr(v) == repr(ref)
+    assert (v + 1) - 1 == pytest.approx(ref) and 2 * v == pytest.approx(2 * ref) and -v == -ref
+    assert json.dumps({"psnr": float(v)}) == json.dumps({"psnr": ref})
+    assert m.result() != ref
