@@ -389,6 +389,7 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
     uint32_t r[2][32];
     tmem_ld32(tmem_row, r[0]);
     float sg[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t mq[4] = {0u, 0u, 0u, 0u};   // training: four mask words at a time, ONE 16-byte store per 128 columns
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         uint32_t (&rr)[32] = r[g & 1];
@@ -420,7 +421,10 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
             uint32_t m = 0;
 #pragma unroll
             for (int k = 0; k < 16; ++k) m |= pos_mask2<kHalf>(o[k]) & (0x00010001u << k);
-            mask_row[g] = m;
+            mq[g & 3] = m;
+            // (eight separate 4-byte stores per row and layer, 32 bytes apart across the lanes, cost the training
+            // forward 0.12 ms of 1.1: tools/fwd_train_bench.py, NERFB200_TC_DEBUG=4)
+            if ((g & 3) == 3) *reinterpret_cast<uint4*>(mask_row + (g - 3)) = make_uint4(mq[0], mq[1], mq[2], mq[3]);
         }
         uint8_t* chunk = act + (g >> 1) * 16384;
         const int u0 = (g & 1) * 4;
@@ -889,7 +893,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                 named_bar_sync(1 + t, kTileRows);
                 if (row == 0) mbar_arrive_cluster(act_ready_leader);      // this CTA's operand for job j is ready
                 bool issued = false;
-                if (kTrain && row == 0) {
+                // debug instantiation only (NERFB200_TC_DEBUG=3/4/5): drop the stash stores / the bitmask stores / both,
+                // to attribute the training forward's slowdown over the inference forward (tools/fwd_train_bench.py)
+                const bool no_stash_store = kDbg && (p.dbg_mode == 3 || p.dbg_mode == 5);
+                const bool no_mask_store = kDbg && (p.dbg_mode == 4 || p.dbg_mode == 5);
+                if (kTrain && row == 0 && !no_stash_store) {
                     if (pendA_bytes) { bulk_s2g(pendA_dst, act_saddr, pendA_bytes); issued = true; }
                     if (pendE_bytes) { bulk_s2g(pendE_dst, enc_saddr, pendE_bytes); issued = true; }
                     if (issued) bulk_commit_group();
@@ -906,7 +914,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                 if (j < 10) {
                     if (kTrain) {
                         uint32_t* mrow = nullptr;
-                        if (tstash && j != 8) mrow = reinterpret_cast<uint32_t*>(tstash + kStashMaskOfs) + ((j == 9 ? 8 : j) * 128 + row) * 8;
+                        if (tstash && j != 8 && !no_mask_store) mrow = reinterpret_cast<uint32_t*>(tstash + kStashMaskOfs) + ((j == 9 ? 8 : j) * 128 + row) * 8;
                         if (j == 7) epilogue_cols_packed<kHalf, 8, true, true, false>(tmem_row, s_bias, act, row, mrow, ws4, &sig_acc);
                         else if (j == 8) epilogue_cols_packed<kHalf, 8, false, false, false>(tmem_row, s_bias, act, row);
                         else if (j == 9) epilogue_cols_packed<kHalf, 4, true, false, false>(tmem_row, s_bias, act, row, mrow);

@@ -1,4 +1,7 @@
-"""Developer tool: time the fused forward with and without the training stash."""
+"""Developer tool: time the fused forward with and without the training stash (fine-model shape of a 4096-ray step).
+With NERFB200_TC_DEBUG=3|4|5 the debug instantiation drops the stash stores / the ReLU bitmask stores / both, which
+attributes the training forward's slowdown over the inference forward (results are then meaningless)."""
+import os
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -17,4 +20,5 @@ def run(st, n=10):
     for _ in range(n): nerf._mlp(1, ro, rd, t, _lib.BF16, st)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-print(f"rows {B*S}: inference {run(None):.3f} ms, training (stash {stash.numel()/1e9:.2f} GB) {run(stash):.3f} ms")
+print(f"TC_DEBUG={os.environ.get('NERFB200_TC_DEBUG', '-')} rows {B*S}: inference {run(None):.3f} ms, "
+      f"training (stash {stash.numel()/1e9:.2f} GB) {run(stash):.3f} ms")
