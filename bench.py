@@ -186,12 +186,19 @@ def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_
     def sigma_like(n):       # sigma == 0 for most samples, like a random-init network
         return rnd(n) * 20 * (rnd(n) > 0.6)
 
+    near, far = torch.full((B,), 0.425, device="cuda"), torch.full((B,), 1.275, device="cuda")
+
+    def sorted_t(s, seed):   # ascending sample positions from the path's own samplers (no torch.sort in the launch list)
+        t_c, edges = ru.sample_coarse(Nc, True, True, near, far, None, seed=100 + seed, ray0=0)
+        if s == Nc:
+            return t_c
+        return ru.sample_fine(Nf, ru.compute_weights(sigma_like(B * Nc), t_c), edges, t_c, None, seed=100 + seed, ray0=0)
+
     for key, name, s, need_w in (("composite_coarse", "composite_fwd_kernel<2,full> (coarse, weights out)", Nc, True),
                                  ("composite_fine", "composite_fwd_kernel<6,full> (fine, render: no weights)", S, False),
                                  ("composite_fine_w", "composite_fwd_kernel<6,full> (fine, weights out)", S, True)):
         bpr = (24 if need_w else 20) * s + 20
-        data = [(rnd(B * s, 3), sigma_like(B * s), torch.sort(rnd(B, s) * 0.8 + 0.4, dim=1).values.contiguous())
-                for _ in range(nsets(B * bpr))]
+        data = [(rnd(B * s, 3), sigma_like(B * s), sorted_t(s, i)) for i in range(nsets(B * bpr))]
         wts = torch.empty((B, s), device="cuda") if need_w else None
         prgb, pdep, pacc = torch.empty((B, 3), device="cuda"), torch.empty((B,), device="cuda"), torch.empty((B,), device="cuda")
 
@@ -203,7 +210,6 @@ def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_
                         "GBps": B * bpr / (ms / 1e3) / 1e9, "input_sets": len(data)})
         del data
 
-    near, far = torch.full((B,), 0.425, device="cuda"), torch.full((B,), 1.275, device="cuda")
     for key, name, with_u in (("sample_fine", f"sample_fine_fast_kernel<{Nc},{Nf},sorted> (in-kernel uniforms)", False),
                               ("sample_fine_u", f"sample_fine_fast_kernel<{Nc},{Nf}> (explicit uniforms)", True)):
         # weights + bin edges + t_coarse read, t_sorted written (+ u read)
