@@ -11,7 +11,10 @@
 //      searches) and a scatter through shared memory. If t_coarse is NOT ascending the warp
 //      falls back to a full bitonic sort of the padded concat in shared memory (same result).
 //
-// HBM-bound by design (1800 B/ray at 64/128); in practice the sort network makes it issue-bound.
+// This file holds two kernels: sample_fine_kernel (any Nc multiple of 32, Nf a power of two) as described above
+// (~1.9 k warp instructions per ray: the sort network makes it issue-bound), and sample_fine_fast_kernel for the
+// shapes the reference runs at, which replaces step 3 by a checked linear placement (~600-780 warp instructions
+// per ray; see the comment above it). HBM-bound by design (1.5-2 KB per ray at 64/128), issue-bound in practice.
 #include "common.cuh"
 
 namespace nb {
@@ -228,6 +231,8 @@ sample_fine_kernel(int64_t B, int Nc, const float* __restrict__ bin_weights, con
 //   * number of coarse samples below a fine sample: its bin index plus one compare (each bin holds
 //     exactly one coarse sample);
 //   * coarse samples: the slots the fine samples left empty, in order.
+// SORTED variant (no uniforms given): the kernel draws the order statistics of Nf uniforms directly, u arrives
+// ascending across (lane, e) and the rank among the fine samples is simply the index - no buckets, no atomics.
 // t is monotone in u only up to fp32 rounding across bin boundaries, and t_coarse is caller data, so
 // the placement is CHECKED (no empty slot left, output ascending) and a warp whose check fails redoes
 // the ray with the generic full bitonic sort: the result is always the exact sort.
