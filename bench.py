@@ -194,9 +194,9 @@ def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_
             return t_c
         return ru.sample_fine(Nf, ru.compute_weights(sigma_like(B * Nc), t_c), edges, t_c, None, seed=100 + seed, ray0=0)
 
-    for key, name, s, need_w in (("composite_coarse", "composite_fwd_kernel<2,full> (coarse, weights out)", Nc, True),
-                                 ("composite_fine", "composite_fwd_kernel<6,full> (fine, render: no weights)", S, False),
-                                 ("composite_fine_w", "composite_fwd_kernel<6,full> (fine, weights out)", S, True)):
+    for key, name, s, need_w in (("composite_coarse", f"composite_fwd_kernel<{Nc // 32},full> (coarse, weights out)", Nc, True),
+                                 ("composite_fine", f"composite_fwd_kernel<{S // 32},full> (fine, render: no weights)", S, False),
+                                 ("composite_fine_w", f"composite_fwd_kernel<{S // 32},full> (fine, weights out)", S, True)):
         bpr = (24 if need_w else 20) * s + 20
         data = [(rnd(B * s, 3), sigma_like(B * s), sorted_t(s, i)) for i in range(nsets(B * bpr))]
         wts = torch.empty((B, s), device="cuda") if need_w else None
