@@ -194,7 +194,8 @@ def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_
             return t_c
         return ru.sample_fine(Nf, ru.compute_weights(sigma_like(B * Nc), t_c), edges, t_c, None, seed=100 + seed, ray0=0)
 
-    for key, name, s, need_w in (("composite_coarse", f"composite_fwd_kernel<{Nc // 32},full> (coarse, weights out)", Nc, True),
+    coarse_name = "composite_fwd_kernel<4,full,2 rays/warp>" if Nc == 64 else f"composite_fwd_kernel<{Nc // 32},full>"
+    for key, name, s, need_w in (("composite_coarse", coarse_name + " (coarse, weights out)", Nc, True),
                                  ("composite_fine", f"composite_fwd_kernel<{S // 32},full> (fine, render: no weights)", S, False),
                                  ("composite_fine_w", f"composite_fwd_kernel<{S // 32},full> (fine, weights out)", S, True)):
         bpr = (24 if need_w else 20) * s + 20
@@ -350,7 +351,7 @@ def run_b200(args):
            "(includes the launch gaps, which are comparable to a 15-50 us kernel)")
     tk = (tj.get("hbm_kernels_dram_bytes_per_launch") if os.path.exists(tpath) else None) or {}
     roofline_hbm = [
-        {"kernel": "composite_fwd_kernel<2,full> + <6,full> (coarse with weights, fine without)", "bound": "hbm",
+        {"kernel": "composite_fwd_kernel<4,full,2 rays/warp> + <6,full> (coarse with weights, fine without)", "bound": "hbm",
          "achieved": comp_alone, "peak": pk["hbm"], "unit": "GB/s", "frac": comp_alone / pk["hbm"],
          "traffic": [tk.get("composite_coarse"), tk.get("composite_fine")] if tk else None,
          "us_per_launch": [ca["us"], cf["us"]], "frac_coarse": ca["GBps"] / pk["hbm"], "frac_fine": cf["GBps"] / pk["hbm"],

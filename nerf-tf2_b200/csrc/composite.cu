@@ -41,28 +41,40 @@ __host__ __device__ constexpr int composite_warp_floats(int E) { return (32 * E 
 // flight together); the lanes then read their E consecutive samples from shared memory with vector
 // loads (conflict-free for the strides that occur: 2, 6, 12 and 3x those). The weights go back through
 // the sigma slots and leave as coalesced 16-byte stores.
-// FULL: S == 32*E exactly (64, 128, 192, 256, 384 ... samples), every bound is a compile-time constant.
-template <int E, bool FULL>
+// FULL: the warp's span is exactly 32*E samples (64, 128, 192, 256, 384 ... samples per ray with one ray per warp), so
+// every bound is a compile-time constant. RPW (rays per warp, 1 or 2; 2 needs FULL): with RPW = 2 a warp takes two
+// ADJACENT rays of 16*E samples each - lanes 0-15 the first, 16-31 the second. The two rays are one contiguous span
+// of HBM, so staging is unchanged; the scan and the reductions run over 16-lane segments (one shuffle step fewer) and
+// the per-warp overhead (setup, copies, scan, five reductions, output) is paid once per two rays. Used for S = 64,
+// where that overhead, not HBM, bounded the one-ray-per-warp form (241 warp instructions per ray, 69 % of HBM peak).
+template <int E, bool FULL, int RPW = 1>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(int64_t B, int S_arg, const float* __restrict__ sigma, const float* __restrict__ rgb,
                      const float* __restrict__ t_vals, int white_bg, float* __restrict__ weights,
                      float* __restrict__ pred_rgb, float* __restrict__ pred_depth, float* __restrict__ acc_map) {
+    static_assert(RPW == 1 || (RPW == 2 && FULL), "two rays per warp only with compile-time sizes");
+    constexpr int W = 32 / RPW;                       // lanes per ray
     extern __shared__ __align__(16) float comp_smem[];
     const int lane = threadIdx.x & 31;
-    const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (ray >= B) return;   // whole warp exits together; no block-level barriers below
+    const int64_t ray0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * RPW;   // first ray of this warp
+    if (ray0 >= B) return;   // whole warp exits together; no block-level barriers below
     float* s_t = comp_smem + (threadIdx.x >> 5) * composite_warp_floats(E);
     float* s_sg = s_t + (32 * E + 4);
     float* s_rgb = s_sg + 32 * E;
-    const int S = FULL ? 32 * E : S_arg;
-    const int64_t base = ray * S;
-    const int s0 = lane * E;
+    const int S = FULL ? W * E : S_arg;               // samples per ray
+    const int nrays = (RPW == 2 && ray0 + 1 < B) ? 2 : 1;
+    const int span = nrays * S;                       // samples this warp stages
+    const int64_t base = ray0 * S;
+    const int s0 = lane * E;                          // position in the warp's span
+    const int ls = (lane % W) * E;                    // position in the lane's ray
+    const int64_t ray = ray0 + lane / W;
+    const bool live = (lane / W) < nrays;             // false for the second half of an odd last warp
 
     const bool vec = ((S & 3) == 0) &&
                      ((((uintptr_t)sigma | (uintptr_t)rgb | (uintptr_t)t_vals | (uintptr_t)weights) & 15) == 0);
-    warp_cp_async<32 * E>(s_t, t_vals + base, S, vec, lane);
-    warp_cp_async<32 * E>(s_sg, sigma + base, S, vec, lane);
-    warp_cp_async<96 * E>(s_rgb, rgb + 3 * base, 3 * S, vec, lane);
+    warp_cp_async<32 * E>(s_t, t_vals + base, span, vec, lane);
+    warp_cp_async<32 * E>(s_sg, sigma + base, span, vec, lane);
+    warp_cp_async<96 * E>(s_rgb, rgb + 3 * base, 3 * span, vec, lane);
     cp_async_wait_all();
     __syncwarp();
 
@@ -80,34 +92,35 @@ composite_fwd_kernel(int64_t B, int S_arg, const float* __restrict__ sigma, cons
     float lane_prod = 1.f;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        int s = s0 + e;
+        const int s = ls + e;
+        const bool in = live && s < S;
         float delta = (s == S - 1) ? 1e10f : __fsub_rn(t[e + 1], t[e]);           // :462-468
         float a = __fsub_rn(1.f, expf(-__fmul_rn(sg[e], delta)));                  // :423
-        a = s < S ? a : 0.f;
+        a = in ? a : 0.f;
         alpha[e] = a;
-        f[e] = s < S ? __fadd_rn(__fsub_rn(1.f, a), 1e-10f) : 1.f;                 // :480
+        f[e] = in ? __fadd_rn(__fsub_rn(1.f, a), 1e-10f) : 1.f;                   // :480
         lane_prod *= f[e];
     }
-    // exclusive scan (product) of lane totals
+    // exclusive scan (product) of lane totals, per ray
     float incl = lane_prod;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        float v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl *= v;
+    for (int o = 1; o < W; o <<= 1) {
+        float v = __shfl_up_sync(0xffffffffu, incl, o, W);
+        if ((lane % W) >= o) incl *= v;
     }
-    float T = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) T = 1.f;
+    float T = __shfl_up_sync(0xffffffffu, incl, 1, W);
+    if ((lane % W) == 0) T = 1.f;
 
     float cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, acc = 0.f;
     float c[3 * E], wv[E];
     load_row<3 * E>(c, s_rgb + 3 * s0);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        int s = s0 + e;
+        const int s = ls + e;
         float w = alpha[e] * T;
         T *= f[e];
         wv[e] = w;
-        if (s < S) {
+        if (live && s < S) {
             cr += w * c[3 * e + 0];
             cg += w * c[3 * e + 1];
             cb += w * c[3 * e + 2];
@@ -116,7 +129,14 @@ composite_fwd_kernel(int64_t B, int S_arg, const float* __restrict__ sigma, cons
         }
     }
     if (weights) store_row<E>(s_sg + s0, wv);   // this lane's own slots: already consumed above
-    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); dep = warp_sum(dep); acc = warp_sum(acc);
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {       // butterfly over the ray's lanes
+        cr += __shfl_xor_sync(0xffffffffu, cr, o);
+        cg += __shfl_xor_sync(0xffffffffu, cg, o);
+        cb += __shfl_xor_sync(0xffffffffu, cb, o);
+        dep += __shfl_xor_sync(0xffffffffu, dep, o);
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
     if (weights) {
         __syncwarp();
         float* wout = weights + base;
@@ -124,14 +144,14 @@ composite_fwd_kernel(int64_t B, int S_arg, const float* __restrict__ sigma, cons
 #pragma unroll
             for (int j = 0; j < (8 * E + 31) / 32; ++j) {
                 const int i = lane + 32 * j;
-                if (i < (S >> 2)) reinterpret_cast<float4*>(wout)[i] = reinterpret_cast<const float4*>(s_sg)[i];
+                if (i < (span >> 2)) reinterpret_cast<float4*>(wout)[i] = reinterpret_cast<const float4*>(s_sg)[i];
             }
         } else {
 #pragma unroll 1
-            for (int i = lane; i < S; i += 32) wout[i] = s_sg[i];
+            for (int i = lane; i < span; i += 32) wout[i] = s_sg[i];
         }
     }
-    if (lane == 0) {
+    if ((lane % W) == 0 && live) {
         if (white_bg) {                                                            // :542-544
             float bg = __fsub_rn(1.f, acc);
             cr += bg; cg += bg; cb += bg;
@@ -253,6 +273,16 @@ int nerfb200_composite_fwd(int64_t B, int S, const float* sigma, const float* rg
     NB_CHECK_ARG(B >= 0 && S >= 2 && S <= 1024, "composite_fwd: need 2 <= S <= 1024, got S=%d", S);
     if (B == 0) return 0;
     NB_CHECK_ARG(sigma && rgb && t_vals && pred_rgb && pred_depth && acc_map, "composite_fwd: NULL pointer");
+    if (S == 64) {
+        // two adjacent rays per warp, a half-warp each (E = 4 samples per lane)
+        constexpr int smem2 = kWarpsPerBlock * composite_warp_floats(4) * (int)sizeof(float);
+        const int64_t warps = (B + 1) / 2;
+        composite_fwd_kernel<4, true, 2><<<(unsigned)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock), kWarpsPerBlock * 32, smem2,
+                                           (cudaStream_t)stream>>>(B, S, sigma, rgb, t_vals, white_bg, weights, pred_rgb, pred_depth,
+                                                                   acc_map);
+        NB_LAUNCH_CHECK();
+        return 0;
+    }
     unsigned grid = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
     NB_DISPATCH_E(pick_E(S), {
         constexpr int smem = kWarpsPerBlock * composite_warp_floats(E) * (int)sizeof(float);
