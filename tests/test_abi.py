@@ -49,6 +49,10 @@ def test_argument_validation_needs_no_gpu():
     assert lib.nerfb200_sample_fine(4, 64, 100, 1, 1, 1, None, 0, 0, 1, None, None, None, None) == 10002
     assert lib.nerfb200_mlp_forward(None, 0, 1, 1, None, None, None, None, None, None, 1, None, None, None) == 10001
     assert lib.nerfb200_get_rays(0, 4, None, None, 0, 0, None, None, None) == 10001
+    # the phase-split backward validates like mlp_backward: no context -> EINVAL, before any CUDA call
+    assert lib.nerfb200_mlp_backward_data(None, 0, 1, 1, None, None, None, 1, None, None, 0, None) == 10001
+    assert lib.nerfb200_mlp_backward_weights(None, 0, 1, 1, None, 1, None, None, 0, None) == 10001
+    assert b"context" in lib.nerfb200_last_error()
     assert lib.nerfb200_mlp_workspace_bytes(1000, 1, 0) == 0
     assert lib.nerfb200_mlp_stash_bytes(10, 0) == 10 * (63 + 27 + 8 * 256 + 256 + 128 + 3 + 1) * 4
 
