@@ -49,6 +49,30 @@ __global__ void __launch_bounds__(128, 1) bulk_kernel(uint8_t* __restrict__ dst,
     }
 }
 
+// The training kernels' store pattern: per SM two "slots"; each slot ships its 64 KB activation buffer with one bulk
+// store, waits until the engine has READ the buffer (wait_group.read 0), then spends `idle` cycles refilling it (the
+// epilogue) before it can ship again. Achieved bandwidth vs idle time tells how much of the stash cost is the
+// store/refill serialisation and how much a deeper staging buffer could recover.
+__global__ void __launch_bounds__(64, 1) bursty_kernel(uint8_t* __restrict__ dst, size_t npieces, int idle) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    constexpr int kBuf = 65536;
+    const int slot = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 2 * kBuf / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = i;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t s = (uint32_t)__cvta_generic_to_shared(sm + slot * kBuf);
+        for (size_t p = (size_t)blockIdx.x * 2 + slot; p < npieces; p += (size_t)gridDim.x * 2) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + p * (size_t)kBuf), "r"(s), "r"(kBuf) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            const long long t0 = clock64();
+            while (clock64() - t0 < idle) { }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 int main() {
     const size_t bytes = (size_t)4 << 30;
     uint8_t *a, *b;
@@ -89,6 +113,12 @@ int main() {
         TIME(nm, bytes, (bulk_kernel<false><<<sms, 128, piece>>>(b, bytes / piece, piece)));
         snprintf(nm, sizeof nm, "cp.async.bulk + L2 evict_first hint, %d B pieces", piece);
         TIME(nm, bytes, (bulk_kernel<true><<<sms, 128, piece>>>(b, bytes / piece, piece)));
+    }
+    cudaFuncSetAttribute(bursty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536);
+    for (int idle : {0, 1000, 2000, 3000, 5000}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "2 slots/SM: 64 KB store, wait read, refill %d cycles", idle);
+        TIME(nm, bytes, (bursty_kernel<<<sms, 64, 2 * 65536>>>(b, bytes / 65536, idle)));
     }
     TIME("copy (ld.cs + st), payload counted once", bytes, (copy_kernel<<<sms * 8, 512>>>((const uint4*)a, (uint4*)b, n16)));
     printf("(copy moves 2x its payload: read + write)\n");
