@@ -41,6 +41,8 @@ extern "C" {
 #define NERFB200_FP32 0   /* fp32 FMA on CUDA cores: the exact-arithmetic check path        */
 #define NERFB200_BF16 1   /* bf16 operands, fp32 accumulate, tcgen05/TMEM fused kernel       */
 #define NERFB200_FP16 2   /* fp16 operands, fp32 accumulate, tcgen05/TMEM fused kernel       */
+#define NERFB200_TF32 3   /* tf32 operands (tcgen05 kind::tf32), fp32 accumulate: what TensorFlow's fp32 MatMul is on
+                             Ampere-and-later GPUs (core/model.py:366-387 Dense layers); render path only */
 
 #define NERFB200_COARSE 0
 #define NERFB200_FINE   1
@@ -107,6 +109,19 @@ NERFB200_API int nerfb200_destroy(nerfb200_ctx* ctx);
  * tensor-core operand image (K-major 128B-swizzled UMMA tiles, bf16 and fp16 copies).
  * Must be called after every optimiser step before the next forward. */
 NERFB200_API int nerfb200_pack_weights(nerfb200_ctx* ctx, const float* flat_params, void* stream);
+/* Context options.
+ *   NERFB200_OPT_PRECISE_LAST (default 1): tensor-core forwards recompute sigma of the LAST sample of every
+ *     ray (row ray*S + S-1, S >= 2) with error-compensated split operands, because the reference's
+ *     delta_last = 1e10 (utils/ray_utils.py:459-468) turns a rounding-induced sign flip of that one ReLU
+ *     output into a jump of alpha_last from 0 to 1.
+ *   NERFB200_OPT_PACK_MASK (default 7): precisions pack_weights produces images for, bit 0 bf16, bit 1 fp16,
+ *     bit 2 tf32 (a training loop packs after every step and needs only its own precision).
+ *   NERFB200_OPT_DEBUG (default 0): developer cycle counters of the fused forward (tools/tc_debug.py).
+ * PRECISE_LAST and PACK_MASK take effect at the next nerfb200_pack_weights. */
+#define NERFB200_OPT_PRECISE_LAST 1
+#define NERFB200_OPT_PACK_MASK    2
+#define NERFB200_OPT_DEBUG        3
+NERFB200_API int nerfb200_set_option(nerfb200_ctx* ctx, int option, int value);
 
 /* ---- a4+a5: fused encoding + 8x256 MLP forward (core/model.py:334-394) -------------------
  * rows are generated on the fly from rays: xyz = o + t*d, dir = d. Outputs rgb[R,3] (sigmoid)

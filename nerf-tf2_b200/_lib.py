@@ -12,8 +12,10 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnerfb200.so")
 
-FP32, BF16, FP16 = 0, 1, 2
-PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
+FP32, BF16, FP16, TF32 = 0, 1, 2, 3
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16, "tf32": TF32}
+PACK_BIT = {BF16: 1, FP16: 2, TF32: 4}          # NERFB200_OPT_PACK_MASK bits
+OPT_PRECISE_LAST, OPT_PACK_MASK, OPT_DEBUG = 1, 2, 3
 COARSE, FINE = 0, 1
 PARAMS_PER_MODEL = 595844
 PARAMS_TOTAL = 2 * PARAMS_PER_MODEL
@@ -35,6 +37,7 @@ SIGNATURES = {
     "nerfb200_create": (_i32, [C.POINTER(_vp)]),
     "nerfb200_destroy": (_i32, [_vp]),
     "nerfb200_pack_weights": (_i32, [_vp, _vp, _vp]),
+    "nerfb200_set_option": (_i32, [_vp, _i32, _i32]),
     "nerfb200_mlp_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "nerfb200_mlp_stash_bytes": (_i64, [_i64, _i32]),
     "nerfb200_mlp_forward": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -89,8 +92,9 @@ def require_cuda():
         raise NerfB200Error("a CUDA device (B200, sm_100a) is required: there is no CPU fallback")
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """The current torch stream of `device` (default: the current device) as a cudaStream_t."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t, dtype=torch.float32, allow_none=False):

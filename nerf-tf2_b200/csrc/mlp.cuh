@@ -6,11 +6,18 @@ struct nerfb200_ctx {
     int device = 0;
     int num_sms = 148;
     // tensor-core operand images, one per (precision, model): see mlp_tc.cu for the layout
-    void* packed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [bf16|fp16][coarse|fine]
+    void* packed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [bf16|fp16][coarse|fine]
+    void* packed_lo[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // W - fl16(W): the split launch of the last-sample rows
     void* packed_bwd[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // W^T images for backward-data
-    float* head_params[2] = {nullptr, nullptr};                       // fp32 biases + sigma head per model
+    void* packed_tf32[2] = {nullptr, nullptr};                          // tf32 image per model (mlp_tc_tf32.cu)
+    float* head_params[2] = {nullptr, nullptr};                         // fp32 biases + sigma head per model
     bool packed_valid = false;
-    int replicas = 1;                                                 // identical copies of each packed image
+    int packed_mask = 0;            // precisions the current images were packed for
+    bool packed_precise = false;    // ... and whether the lo images were packed with them
+    // options (nerfb200_set_option)
+    int precise_last = 1;           // NERFB200_OPT_PRECISE_LAST
+    int pack_mask = 7;              // NERFB200_OPT_PACK_MASK: bit 0 bf16, bit 1 fp16, bit 2 tf32
+    int debug = 0;                  // NERFB200_OPT_DEBUG: cycle-counter instantiation of the pair kernel
 };
 
 namespace nb {
@@ -32,6 +39,16 @@ int tc_train_pack(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st);
 int tc_create(nerfb200_ctx* ctx);
 void tc_destroy(nerfb200_ctx* ctx);
 int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st);
+int check_device(const nerfb200_ctx* ctx, const char* fn);
+// mlp_tc_tf32.cu: the kind::tf32 render kernel (inference only)
+int tf32_create(nerfb200_ctx* ctx);
+void tf32_destroy(nerfb200_ctx* ctx);
+int tf32_pack(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st);
+int tf32_forward(nerfb200_ctx* ctx, int which, int64_t B, int S, const float* ro, const float* rd, const float* t,
+                 float* rgb, float* sigma, cudaStream_t st);
+// sigma of the last sample of every ray with split (hi + lo) 16-bit operands; no-op when the option is off or S < 2
+int tc_precise_last(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
+                    float* sigma, void* stash, cudaStream_t st);
 int64_t tc_workspace_bytes(int64_t R, int training);
 int64_t tc_stash_bytes(int64_t R);
 int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd,

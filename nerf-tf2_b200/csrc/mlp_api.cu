@@ -27,13 +27,29 @@ int nerfb200_pack_weights(nerfb200_ctx* ctx, const float* flat_params, void* str
     return tc_pack_weights(ctx, flat_params, (cudaStream_t)stream);
 }
 
+int nerfb200_set_option(nerfb200_ctx* ctx, int option, int value) {
+    NB_CHECK_ARG(ctx != nullptr, "set_option: NULL context");
+    switch (option) {
+        case NERFB200_OPT_PRECISE_LAST: ctx->precise_last = value != 0; return 0;
+        case NERFB200_OPT_PACK_MASK:
+            NB_CHECK_ARG(value >= 1 && value <= 7, "set_option(PACK_MASK): value must be a non-empty subset of bits 0..2");
+            ctx->pack_mask = value;
+            return 0;
+        case NERFB200_OPT_DEBUG: ctx->debug = value; return 0;
+        default: NB_CHECK_ARG(false, "set_option: unknown option %d", option);
+    }
+    return 0;
+}
+
 int64_t nerfb200_mlp_workspace_bytes(int64_t R, int precision, int training) {
     if (R < 0) return -1;
+    if (precision == NERFB200_TF32) return 0;
     return precision == NERFB200_FP32 ? ref_workspace_bytes(R, training) : tc_workspace_bytes(R, training);
 }
 
 int64_t nerfb200_mlp_stash_bytes(int64_t R, int precision) {
     if (R < 0) return -1;
+    if (precision == NERFB200_TF32) return 0;
     return precision == NERFB200_FP32 ? ref_stash_bytes(R) : tc_stash_bytes(R);
 }
 
@@ -41,7 +57,7 @@ static int check_common(const char* fn, nerfb200_ctx* ctx, int which, int64_t B,
     NB_CHECK_ARG(ctx != nullptr, "%s: NULL context", fn);
     NB_CHECK_ARG(which == NERFB200_COARSE || which == NERFB200_FINE, "%s: which must be 0 (coarse) or 1 (fine)", fn);
     NB_CHECK_ARG(B >= 0 && S >= 1, "%s: bad shape B=%lld S=%d", fn, (long long)B, S);
-    NB_CHECK_ARG(precision >= NERFB200_FP32 && precision <= NERFB200_FP16, "%s: unknown precision %d", fn, precision);
+    NB_CHECK_ARG(precision >= NERFB200_FP32 && precision <= NERFB200_TF32, "%s: unknown precision %d", fn, precision);
     return 0;
 }
 
@@ -58,6 +74,10 @@ int nerfb200_mlp_forward(nerfb200_ctx* ctx, int which, int64_t B, int S, const f
         return ref_forward(st, flat_params + (int64_t)which * kParamsPerModel, B, S, rays_o, rays_d, t_vals, rgb, sigma,
                            workspace, stash);
     }
+    if (precision == NERFB200_TF32) {
+        if (stash) { set_error("mlp_forward: tf32 is a render precision; training uses bf16, fp16 or fp32"); return NERFB200_ENOTSUP; }
+        return tf32_forward(ctx, which, B, S, rays_o, rays_d, t_vals, rgb, sigma, st);
+    }
     return tc_forward(ctx, which, precision == NERFB200_FP16, B, S, rays_o, rays_d, t_vals, rgb, sigma, workspace, stash, st);
 }
 
@@ -67,6 +87,7 @@ int nerfb200_mlp_backward(nerfb200_ctx* ctx, int which, int64_t B, int S, const 
     int rc = check_common("mlp_backward", ctx, which, B, S, precision);
     if (rc) return rc;
     NB_CHECK_ARG(flat_params && d_rgb && d_sigma && flat_grads, "mlp_backward: NULL tensor");
+    if (precision == NERFB200_TF32) { set_error("mlp_backward: tf32 is a render precision; training uses bf16, fp16 or fp32"); return NERFB200_ENOTSUP; }
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == NERFB200_FP32)
@@ -80,8 +101,8 @@ int nerfb200_mlp_backward_data(nerfb200_ctx* ctx, int which, int64_t B, int S, c
                                const float* d_sigma, int precision, void* workspace, void* stash, int max_sms, void* stream) {
     int rc = check_common("mlp_backward_data", ctx, which, B, S, precision);
     if (rc) return rc;
-    if (precision == NERFB200_FP32) {
-        set_error("mlp_backward_data: the phase-split backward exists for the tensor-core precisions only");
+    if (precision == NERFB200_FP32 || precision == NERFB200_TF32) {
+        set_error("mlp_backward_data: the phase-split backward exists for the 16-bit tensor-core precisions only");
         return NERFB200_ENOTSUP;
     }
     NB_CHECK_ARG(flat_params && d_rgb && d_sigma && max_sms >= 0, "mlp_backward_data: bad argument");
@@ -94,8 +115,8 @@ int nerfb200_mlp_backward_weights(nerfb200_ctx* ctx, int which, int64_t B, int S
                                   void* workspace, void* stash, int max_sms, void* stream) {
     int rc = check_common("mlp_backward_weights", ctx, which, B, S, precision);
     if (rc) return rc;
-    if (precision == NERFB200_FP32) {
-        set_error("mlp_backward_weights: the phase-split backward exists for the tensor-core precisions only");
+    if (precision == NERFB200_FP32 || precision == NERFB200_TF32) {
+        set_error("mlp_backward_weights: the phase-split backward exists for the 16-bit tensor-core precisions only");
         return NERFB200_ENOTSUP;
     }
     NB_CHECK_ARG(flat_grads && max_sms >= 0, "mlp_backward_weights: bad argument");

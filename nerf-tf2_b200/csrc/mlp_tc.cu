@@ -50,7 +50,6 @@ struct Chunk {
 };
 
 constexpr int kNumJobs = 11;
-constexpr int kDefaultReplicas = 1, kMaxReplicas = 32;   // replicas of the image: measured no effect (L2 serves the shared stream fine)
 constexpr int kMaxChunks = 80;
 
 constexpr uint32_t kBiasTileBytes = 2048;   // one CTA's share of a layer's bias as a tensor-core B operand (see pack_bias_tiles_kernel)
@@ -122,7 +121,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v
 template <> __device__ __forceinline__ __half to16<__half>(float v) { return __float2half_rn(v); }
 
 // One thread per 16-byte unit of the packed image.
-template <typename T>
+template <typename T, bool kLo>
 __global__ void pack_weights_kernel(const float* __restrict__ P /* one model */, uint8_t* __restrict__ img, int nchunks) {
     int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // locate chunk by linear scan over the table (<= 80 entries)
@@ -155,6 +154,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ P /* one model */,
         float v = 0.f;
         if (k >= 0 && k < dim.fan_in && n < dim.fan_out) v = W[(int64_t)k * dim.fan_out + n];
         vals[e] = to16<T>(v);
+        if (kLo) vals[e] = to16<T>(v - (float)vals[e]);      // lo image of the split launch: what the 16-bit rounding dropped
     }
     *reinterpret_cast<uint4*>(img + byte) = *reinterpret_cast<uint4*>(vals);
 }
@@ -222,12 +222,12 @@ constexpr int kProducerWarp = 8, kMmaWarp = 9;   // highest warp ids: the per-SM
                                                  // and the single MMA-issuing thread is the critical path
 
 struct TcParams {
-    const uint8_t* wimg;     // packed weights of this model/precision (replica 0)
-    uint32_t wimg_stride;    // bytes between replicas
+    const uint8_t* wimg;     // packed weights of this model/precision
+    const uint8_t* wimg_lo;  // split instantiation: the image of W - fl16(W) (same layout), else NULL
     uint32_t bias_ofs;       // byte offset of the bias tiles inside the image
-    int replicas;            // CTAs spread their weight reads over this many identical copies
-    unsigned long long* dbg; // optional cycle counters of block 0 (NERFB200_TC_DEBUG), else NULL
-    int dbg_mode;            // developer experiments (NERFB200_TC_DEBUG value): 2 = skip epilogue math
+    int last_only;           // split instantiation: row r of the launch is the LAST sample of ray r (row r*S + S-1)
+    unsigned long long* dbg; // optional cycle counters (debug instantiation, nerfb200_set_option), else NULL
+    int dbg_mode;            // debug instantiation: 3/4/5 = drop the stash stores / the bitmask stores / both
     const float* heads;      // HeadOffsets block
     const float* ro; const float* rd; const float* t;
     float* rgb; float* sigma;
@@ -269,12 +269,19 @@ __device__ __forceinline__ void sincos_octaves(float x, float* e) {
 
 // Loads the ray of this thread's row, forms xyz = o + t*d (utils/ray_utils.py:251) and writes the
 // L=10 positional encoding (core/model.py:305-332) into the 64-column encoding buffer (col 63 = 0).
-template <bool kHalf>
-__device__ __forceinline__ void prep_tile(const TcParams& p, int tile, int row, uint8_t* enc, RowCtx& rc) {
+template <bool kHalf, bool kSplit = false>
+__device__ __forceinline__ void prep_tile(const TcParams& p, int tile, int row, uint8_t* enc, RowCtx& rc, uint8_t* enc_lo = nullptr) {
     rc.grow = (int64_t)tile * kTileRows + row;
     rc.valid = rc.grow < p.R;
-    const int64_t lrow = rc.valid ? rc.grow : p.R - 1;
-    const int64_t ray = (p.R <= 0x7fffffffLL) ? (int64_t)((uint32_t)lrow / (uint32_t)p.S) : lrow / p.S;
+    int64_t lrow = rc.valid ? rc.grow : p.R - 1;
+    int64_t ray;
+    if (kSplit) {           // the launch's row r is the last sample of ray r
+        ray = lrow;
+        lrow = lrow * p.S + (p.S - 1);
+        rc.grow = lrow;
+    } else {
+        ray = (p.R <= 0x7fffffffLL) ? (int64_t)((uint32_t)lrow / (uint32_t)p.S) : lrow / p.S;
+    }
     const float tv = __ldg(p.t + lrow);
     float xyz[3];
 #pragma unroll
@@ -295,6 +302,14 @@ __device__ __forceinline__ void prep_tile(const TcParams& p, int tile, int row, 
         v.z = pack2<kHalf>(e[8 * u + 4], e[8 * u + 5]);
         v.w = pack2<kHalf>(e[8 * u + 6], e[8 * u + 7]);
         *reinterpret_cast<uint4*>(enc + swz(row, u)) = v;
+        if (kSplit) {       // the part of the encoding that the 16-bit rounding dropped
+            uint4 w;
+            w.x = pack2<kHalf>(e[8 * u + 0] - unpack_lo<kHalf>(v.x), e[8 * u + 1] - unpack_hi<kHalf>(v.x));
+            w.y = pack2<kHalf>(e[8 * u + 2] - unpack_lo<kHalf>(v.y), e[8 * u + 3] - unpack_hi<kHalf>(v.y));
+            w.z = pack2<kHalf>(e[8 * u + 4] - unpack_lo<kHalf>(v.z), e[8 * u + 5] - unpack_hi<kHalf>(v.z));
+            w.w = pack2<kHalf>(e[8 * u + 6] - unpack_lo<kHalf>(v.w), e[8 * u + 7] - unpack_hi<kHalf>(v.w));
+            *reinterpret_cast<uint4*>(enc_lo + swz(row, u)) = w;
+        }
     }
     fence_proxy_async();
 }
@@ -320,64 +335,6 @@ __device__ __forceinline__ void write_enc_dir(const float (&dir)[3], uint8_t* en
         *reinterpret_cast<uint4*>(enc + swz(row, u)) = v4;
     }
 }
-
-// One layer's epilogue for this thread's row: NG groups of 32 accumulator columns
-// TMEM -> registers (double-buffered: the load of group g+1 is in flight while g is processed)
-// -> + bias (smem broadcast) -> ReLU -> 16-bit -> swizzled smem = next layer's A operand.
-template <bool kHalf, int NG, bool kRelu, bool kSigma>
-__device__ __forceinline__ void epilogue_cols(uint32_t tmem_row, const float* s_bias, uint8_t* act, int row,
-                                              const float4* ws4, float& sig_acc, uint32_t* mask_row = nullptr) {
-    uint32_t r[2][32];
-    tmem_ld32(tmem_row, r[0]);
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        uint32_t (&rr)[32] = r[g & 1];
-        tmem_ld_wait(rr);
-        if (g + 1 < NG) tmem_ld32(tmem_row + (uint32_t)(32 * (g + 1)), r[(g + 1) & 1]);
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias + 32 * g);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 bb = b4[i];
-            v[4 * i + 0] = __uint_as_float(rr[4 * i + 0]) + bb.x;
-            v[4 * i + 1] = __uint_as_float(rr[4 * i + 1]) + bb.y;
-            v[4 * i + 2] = __uint_as_float(rr[4 * i + 2]) + bb.z;
-            v[4 * i + 3] = __uint_as_float(rr[4 * i + 3]) + bb.w;
-        }
-        if (kRelu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-            if (mask_row) {   // training: ReLU bitmask of this group for the backward pass
-                uint32_t m = 0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f) ? (1u << mask_bit(i)) : 0u;
-                mask_row[g] = m;
-            }
-        }
-        if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 w = __ldg(ws4 + 8 * g + i);
-                sig_acc = fmaf(v[4 * i + 0], w.x, sig_acc);
-                sig_acc = fmaf(v[4 * i + 1], w.y, sig_acc);
-                sig_acc = fmaf(v[4 * i + 2], w.z, sig_acc);
-                sig_acc = fmaf(v[4 * i + 3], w.w, sig_acc);
-            }
-        }
-        uint8_t* chunk = act + (g >> 1) * 16384;
-        const int u0 = (g & 1) * 4;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            uint4 o;
-            o.x = pack2<kHalf>(v[8 * u + 0], v[8 * u + 1]);
-            o.y = pack2<kHalf>(v[8 * u + 2], v[8 * u + 3]);
-            o.z = pack2<kHalf>(v[8 * u + 4], v[8 * u + 5]);
-            o.w = pack2<kHalf>(v[8 * u + 6], v[8 * u + 7]);
-            *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = o;
-        }
-    }
-}
-
 
 
 // Inference epilogue with packed arithmetic: add.f32x2 for the bias and ONE conversion per pair with the
@@ -423,7 +380,7 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
             for (int k = 0; k < 16; ++k) m |= pos_mask2<kHalf>(o[k]) & (0x00010001u << k);
             mq[g & 3] = m;
             // (eight separate 4-byte stores per row and layer, 32 bytes apart across the lanes, cost the training
-            // forward 0.12 ms of 1.1: tools/fwd_train_bench.py, NERFB200_TC_DEBUG=4)
+            // forward 0.12 ms of 1.1: tools/fwd_train_bench.py, NERFB200_OPT_DEBUG mode 4)
             if ((g & 3) == 3) *reinterpret_cast<uint4*>(mask_row + (g - 3)) = make_uint4(mq[0], mq[1], mq[2], mq[3]);
         }
         uint8_t* chunk = act + (g >> 1) * 16384;
@@ -435,257 +392,47 @@ __device__ __forceinline__ void epilogue_cols_packed(uint32_t tmem_row, const fl
     if (kSigma) *sig_acc += (sg[0] + sg[1]) + (sg[2] + sg[3]);
 }
 
+// Split instantiation (last-sample rows, see mlp_tc_forward_pair_kernel): the post-ReLU activation leaves as TWO
+// 16-bit images, hi = fl16(v) and lo = fl16(v - hi), so that the next layer's three MMAs hi.Whi + lo.Whi + hi.Wlo
+// carry ~16 (bf16) / ~22 (fp16) significand bits instead of 8 / 11.
+template <bool kHalf, bool kSigma>
+__device__ __forceinline__ void epilogue_cols_split(uint32_t tmem_row, uint8_t* act_hi, uint8_t* act_lo, int row,
+                                                    const float4* ws4, float* sig_acc) {
+    uint32_t r[2][32];
+    tmem_ld32(tmem_row, r[0]);
+    float sg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        uint32_t (&rr)[32] = r[g & 1];
+        tmem_ld_wait(rr);
+        if (g + 1 < 8) tmem_ld32(tmem_row + (uint32_t)(32 * (g + 1)), r[(g + 1) & 1]);
+        uint32_t oh[16], ol[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float v0 = fmaxf(__uint_as_float(rr[4 * i + 0]), 0.f), v1 = fmaxf(__uint_as_float(rr[4 * i + 1]), 0.f);
+            const float v2 = fmaxf(__uint_as_float(rr[4 * i + 2]), 0.f), v3 = fmaxf(__uint_as_float(rr[4 * i + 3]), 0.f);
+            if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
+                const float4 w = __ldg(ws4 + 8 * g + i);
+                sg[0] = fmaf(v0, w.x, sg[0]); sg[1] = fmaf(v1, w.y, sg[1]);
+                sg[2] = fmaf(v2, w.z, sg[2]); sg[3] = fmaf(v3, w.w, sg[3]);
+            }
+            oh[2 * i] = pack2<kHalf>(v0, v1);
+            oh[2 * i + 1] = pack2<kHalf>(v2, v3);
+            ol[2 * i] = pack2<kHalf>(v0 - unpack_lo<kHalf>(oh[2 * i]), v1 - unpack_hi<kHalf>(oh[2 * i]));
+            ol[2 * i + 1] = pack2<kHalf>(v2 - unpack_lo<kHalf>(oh[2 * i + 1]), v3 - unpack_hi<kHalf>(oh[2 * i + 1]));
+        }
+        const int cofs = (g >> 1) * 16384, u0 = (g & 1) * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            *reinterpret_cast<uint4*>(act_hi + cofs + swz(row, u0 + u)) = make_uint4(oh[4 * u], oh[4 * u + 1], oh[4 * u + 2], oh[4 * u + 3]);
+            *reinterpret_cast<uint4*>(act_lo + cofs + swz(row, u0 + u)) = make_uint4(ol[4 * u], ol[4 * u + 1], ol[4 * u + 2], ol[4 * u + 3]);
+        }
+    }
+    if (kSigma) *sig_acc += (sg[0] + sg[1]) + (sg[2] + sg[3]);
+}
+
 #define NB_T0() long long _t0 = dbg_on ? clock64() : 0
 #define NB_T1(slot) do { if (dbg_on) dbg_acc##slot += (unsigned long long)(clock64() - _t0); } while (0)
-
-template <bool kHalf, bool kTrain>
-__global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcParams p) {
-    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
-    unsigned long long dbg_acc0 = 0, dbg_acc1 = 0, dbg_acc2 = 0, dbg_acc3 = 0;
-    const long long t_kernel0 = clock64();
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t sbase = smem_u32(smem);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
-    // barrier indices
-    auto ring_full = [&](int s) { return sbase + kSmemBar + 8 * s; };
-    auto ring_empty = [&](int s) { return sbase + kSmemBar + 8 * (kStages + s); };
-    auto act_ready = [&](int t) { return sbase + kSmemBar + 8 * (2 * kStages + t); };
-    auto acc_full = [&](int t) { return sbase + kSmemBar + 8 * (2 * kStages + 2 + t); };
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(act_ready(t), kTileRows); mbar_init(acc_full(t), 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-
-    const int pairs = (p.num_tiles + 1) >> 1;
-    constexpr int fmt = kHalf ? 0 : 1;
-
-    if (warp == kProducerWarp) {
-        // ===================== weight producer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            // every CTA streams the same 1.2 MB image; spreading the CTAs over a few identical copies
-            // spreads the reads over more L2 slices (otherwise all SMs hit the same lines in lockstep)
-            const uint8_t* wimg = p.wimg + (size_t)(blockIdx.x % p.replicas) * p.wimg_stride;
-            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
-                for (int j = 0; j < kNumJobs; ++j) {
-                    for (int t = 0; t < 2; ++t) {
-                        if (pr * 2 + t >= p.num_tiles) continue;
-                        for (int ci = c_job_begin[j]; ci < c_job_begin[j + 1]; ++ci) {
-                            const Chunk ch = c_chunks[ci];
-                            { NB_T0(); mbar_wait(ring_empty(stage), phase ^ 1); NB_T1(0); }
-                            uint32_t bytes = (uint32_t)ch.rows * 128u;
-                            mbar_expect_tx(ring_full(stage), bytes);
-                            bulk_g2s(sbase + kSmemRing + stage * kStageBytes, wimg + ch.gofs, bytes, ring_full(stage));
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == kMmaWarp) {
-        // ===================== MMA issuer =====================
-        // One thread issues every tcgen05.mma of the CTA and its instruction stream is the critical
-        // path: everything it touches lives in registers (no local memory: with the shared-memory
-        // carve-out at its maximum there is almost no L1, so a spilled scalar costs an L2 round trip).
-        if (lane == 0) {
-            const uint32_t sbar = sbase + kSmemBar;
-            const uint32_t ring_lo = ((sbase + kSmemRing) >> 4) & 0x3FFFu;
-            constexpr uint32_t id128 = umma_idesc(fmt, 128), id16 = umma_idesc(fmt, 16);
-            uint32_t stage = 0, phase = 0, act_phase_bits = 0;
-            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
-#pragma unroll 1
-                for (int j = 0; j < kNumJobs; ++j) {
-                    // layer shape: NH halves of N, KC chunks of K=64 per half, enc_kc = chunk fed from the encoding buffer
-                    const int NH = (j >= 9) ? 1 : 2;
-                    const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
-                    const int enc_kc = (j == 0) ? 0 : (j == 5 || j == 9) ? 4 : -1;
-                    const bool enc_short = (j == 9);          // enc_dir is 32 columns: 2 K-steps
-                    const uint32_t idesc = (j == 10) ? id16 : id128;
-#pragma unroll 1
-                    for (int t = 0; t < 2; ++t) {
-                        if (pr * 2 + t >= p.num_tiles) continue;
-                        { NB_T0(); mbar_wait(sbar + 8 * (2 * kStages + t), (act_phase_bits >> t) & 1u); NB_T1(0); }
-                        act_phase_bits ^= 1u << t;
-                        tc_fence_after();
-                        const uint32_t act_lo = ((sbase + kSmemAct + t * kActBytes) >> 4) & 0x3FFFu;
-                        const uint32_t enc_lo = ((sbase + kSmemEnc + t * kEncBytes) >> 4) & 0x3FFFu;
-                        const uint32_t d = tmem_base + (uint32_t)(t * 256);
-#pragma unroll 1
-                        for (int nh = 0; nh < NH; ++nh) {
-                            const uint32_t dd = d + (uint32_t)(nh * 128);
-#pragma unroll 1
-                            for (int kc = 0; kc < KC; ++kc) {
-                                { NB_T0(); mbar_wait(sbar + 8 * stage, phase); NB_T1(1); }
-                                tc_fence_after();
-                                const bool is_enc = kc == enc_kc;
-                                const uint32_t a_lo = is_enc ? enc_lo : act_lo + (uint32_t)(kc * 1024);
-                                const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
-                                umma_f16(dd, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
-                                umma_f16(dd, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
-                                if (!(is_enc && enc_short)) {
-                                    umma_f16(dd, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
-                                    umma_f16(dd, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
-                                }
-                                umma_commit(sbar + 8 * (kStages + stage));
-                                if (++stage == kStages) { stage = 0; phase ^= 1; }
-                            }
-                        }
-                        umma_commit(sbar + 8 * (2 * kStages + 2 + t));
-                    }
-                }
-            }
-        }
-    } else if (warp < 8) {
-        // ===================== epilogue warps =====================
-        const int t = warp >> 2;                       // slot
-        const int q = warp & 3;                        // TMEM lane quadrant of this warp
-        const int row = q * 32 + lane;                 // row inside the tile == TMEM lane
-        uint8_t* act = smem + kSmemAct + t * kActBytes;
-        uint8_t* enc = smem + kSmemEnc + t * kEncBytes;
-        float* s_bias = reinterpret_cast<float*>(smem + kSmemBias + t * 1024);
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
-        uint32_t acc_phase = 0;
-        const float4* ws4 = reinterpret_cast<const float4*>(p.heads + HeadOffsets::wsigma);
-
-        RowCtx cur, nxt;
-        // training: activation images leave through bulk stores issued by one thread per slot; a store is
-        // queued when its source (activation buffer / encoding buffer) has been written and is issued at
-        // the next job boundary, after the slot's barrier has made all 128 threads' writes visible
-        uint8_t* pendA_dst = nullptr; uint32_t pendA_bytes = 0;
-        uint8_t* pendE_dst = nullptr; uint32_t pendE_bytes = 0;
-        const uint32_t act_saddr = sbase + kSmemAct + t * kActBytes, enc_saddr = sbase + kSmemEnc + t * kEncBytes;
-        int pr = blockIdx.x;
-        if (pr < pairs && pr * 2 + t < p.num_tiles) {
-            prep_tile<kHalf>(p, pr * 2 + t, row, enc, cur);
-            if (kTrain) { pendE_dst = p.stash + (size_t)(pr * 2 + t) * kStashTileBytes + kStashChunkEncXyz * 16384; pendE_bytes = 16384; }
-        }
-        for (; pr < pairs; pr += gridDim.x) {
-            const int tile = pr * 2 + t;
-            if (tile >= p.num_tiles) continue;
-            uint8_t* tstash = kTrain ? p.stash + (size_t)tile * kStashTileBytes : nullptr;
-            mbar_arrive(act_ready(t));                 // enc_xyz of this tile is in place (prep_tile fenced)
-
-            float sig_acc = 0.f;
-            for (int j = 0; j < kNumJobs; ++j) {
-                // stage this job's biases in shared memory while the tensor core works
-                long long _tb = dbg_on ? clock64() : 0;
-                named_bar_sync(1 + t, kTileRows);      // all 4 warps are done with the previous job (and its biases)
-                bool issued = false;
-                if (kTrain && row == 0) {
-                    if (pendA_bytes) { bulk_s2g(pendA_dst, act_saddr, pendA_bytes); issued = true; }
-                    if (pendE_bytes) { bulk_s2g(pendE_dst, enc_saddr, pendE_bytes); issued = true; }
-                    if (issued) bulk_commit_group();
-                }
-                pendA_bytes = 0; pendE_bytes = 0;
-                {
-                    const int N = j < 9 ? 256 : (j == 9 ? 128 : 16);
-                    const float* b = p.heads + HeadOffsets::bias(j);
-                    if (row < N) s_bias[row] = __ldg(b + row);
-                    if (row + 128 < N) s_bias[row + 128] = __ldg(b + row + 128);
-                }
-                named_bar_sync(1 + t, kTileRows);
-                if (dbg_on) dbg_acc2 += (unsigned long long)(clock64() - _tb);
-                { NB_T0(); mbar_wait(acc_full(t), acc_phase); NB_T1(0); }
-                acc_phase ^= 1;
-                tc_fence_after();
-                if (kTrain) {
-                    // the bulk stores issued at the job boundary had the whole MMA to drain; their sources are
-                    // overwritten by the epilogue below, so make sure they have been read
-                    if (issued) bulk_wait_read_all();
-                    named_bar_sync(1 + t, kTileRows);
-                }
-                long long _te = dbg_on ? clock64() : 0;
-                if (j < 10 && p.dbg_mode == 2) {
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(act_ready(t));
-                } else if (j < 10) {
-                    uint32_t* mrow = nullptr;
-                    if (kTrain && j != 8)
-                        mrow = reinterpret_cast<uint32_t*>(tstash + kStashMaskOfs) + ((j == 9 ? 8 : j) * 128 + row) * 8;
-                    if (j == 7) epilogue_cols<kHalf, 8, true, true>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
-                    else if (j == 8) epilogue_cols<kHalf, 8, false, false>(tmem_row, s_bias, act, row, ws4, sig_acc);
-                    else if (j == 9) epilogue_cols<kHalf, 4, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
-                    else epilogue_cols<kHalf, 8, true, false>(tmem_row, s_bias, act, row, ws4, sig_acc, mrow);
-                    if (kTrain) {
-                        pendA_dst = tstash + (j < 8 ? stash_chunk_Y(j) : j == 8 ? kStashChunkBott : kStashChunkY9) * 16384;
-                        pendA_bytes = j == 9 ? 2 * 16384 : 4 * 16384;
-                    }
-                    if (j == 5) {
-                        write_enc_dir<kHalf>(cur.dir, enc, row);   // dense_5 has consumed enc_xyz
-                        if (kTrain) { pendE_dst = tstash + kStashChunkEncDir * 16384; pendE_bytes = 16384; }
-                    }
-                    if (j == 7) {
-                        float sg = fmaxf(sig_acc + __ldg(p.heads + HeadOffsets::bsigma), 0.f);
-                        if (cur.valid) p.sigma[cur.grow] = sg;
-                        if (kTrain) reinterpret_cast<float*>(tstash + kStashOutOfs)[3 * 128 + row] = cur.valid ? sg : 0.f;
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(act_ready(t));
-                    if (dbg_on) dbg_acc1 += (unsigned long long)(clock64() - _te);
-                    if (j == 9) {
-                        // dense_9 has consumed enc_dir: encode the NEXT tile of this slot now, off the critical path
-                        const int npr = pr + gridDim.x;
-                        NB_T0();
-                        if (npr < pairs && npr * 2 + t < p.num_tiles) {
-                            prep_tile<kHalf>(p, npr * 2 + t, row, enc, nxt);
-                            if (kTrain) { pendE_dst = p.stash + (size_t)(npr * 2 + t) * kStashTileBytes + kStashChunkEncXyz * 16384; pendE_bytes = 16384; }
-                        }
-                        NB_T1(3);
-                    }
-                } else {
-                    // rgb head: 16 accumulator columns, 3 used (core/model.py:387)
-                    uint32_t r[32];
-                    tmem_ld32(tmem_row, r);   // columns 16..31 hold stale data from dense_9; ignored
-                    tmem_ld_wait(r);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float x = __uint_as_float(r[c]) + s_bias[c];
-                        float y = 1.f / (1.f + expf(-x));
-                        if (cur.valid) p.rgb[3 * cur.grow + c] = y;
-                        if (kTrain) reinterpret_cast<float*>(tstash + kStashOutOfs)[3 * row + c] = cur.valid ? y : 0.f;
-                    }
-                    tc_fence_before();
-                }
-            }
-            cur = nxt;
-        }
-        if (kTrain) {
-            // flush what the last job queued, and do not exit while bulk stores are in flight
-            named_bar_sync(1 + t, kTileRows);
-            if (row == 0) {
-                if (pendA_bytes) bulk_s2g(pendA_dst, act_saddr, pendA_bytes);
-                if (pendE_bytes) bulk_s2g(pendE_dst, enc_saddr, pendE_bytes);
-                bulk_commit_group();
-                bulk_wait_all();
-            }
-        }
-    }
-
-    if (dbg_on && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == 0 || warp == 4)) {
-        // rows: 0 producer, 1 mma, 2 epilogue slot0, 3 epilogue slot1; cols: wait-main, wait-ring/epilogue, bias-bar, prep, total
-        int rowi = warp == kProducerWarp ? 0 : warp == kMmaWarp ? 1 : warp == 0 ? 2 : 3;
-        p.dbg[rowi * 8 + 0] = dbg_acc0; p.dbg[rowi * 8 + 1] = dbg_acc1; p.dbg[rowi * 8 + 2] = dbg_acc2; p.dbg[rowi * 8 + 3] = dbg_acc3;
-        p.dbg[rowi * 8 + 4] = (unsigned long long)(clock64() - t_kernel0);
-    }
-    __syncthreads();
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-    }
-}
 
 
 // =============================================================================================
@@ -696,8 +443,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_forward_kernel(const TcPar
 // Roles per CTA are as in the single-CTA kernel; only the leader's warp 9 issues MMAs, the peer's warp 9
 // relays "my half of the weight stage has landed" to the leader's ring barrier. tcgen05.commit multicasts
 // completion to both CTAs' barriers.
-template <bool kHalf, bool kTrain, bool kDbg>
+//
+// kSplit instantiation -- the last sample of every ray at fp32-grade accuracy. The reference sets delta_last = 1e10
+// (utils/ray_utils.py:459-468), so alpha_last jumps from 0 to 1 when the last sample's ReLU'd sigma leaves zero: a
+// 16-bit rounding error that flips that ONE sign moves the pixel by T_last * (rgb_last - background). A second,
+// small launch therefore recomputes sigma of row ray*S + S-1 of every ray (1 of 64 / 192 rows) through dense_0..7
+// and the sigma head with error-compensated operands: activations and weights are split into hi + lo 16-bit
+// parts (slot 0's buffers hold hi, slot 1's hold lo, of ONE tile per CTA) and every K chunk issues hi.Whi,
+// lo.Whi, hi.Wlo into the same accumulator. Only the sigma of those rows is overwritten.
+template <bool kHalf, bool kTrain, bool kDbg, bool kSplit = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_forward_pair_kernel(const TcParams p) {
+    static_assert(!(kSplit && (kTrain || kDbg)), "the split instantiation is inference-shaped (it patches sigma only)");
+    constexpr int kJobs = kSplit ? 8 : kNumJobs;        // split: dense_0..7 (+ sigma head in the last epilogue)
+    constexpr int kTilesPerCluster = kSplit ? 2 : 4;    // split: one tile per CTA (slot 1's buffers hold the lo parts)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -741,16 +499,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int num_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
-    const int quads = (p.num_tiles + 3) >> 2;          // a cluster works on 4 tiles at a time: 2 slots x 2 CTAs
+    const int quads = (p.num_tiles + kTilesPerCluster - 1) / kTilesPerCluster;   // a cluster works on 4 tiles at a time: 2 slots x 2 CTAs
     constexpr int fmt = kHalf ? 0 : 1;
+    auto slots_of = [&](int qd) { return kSplit ? 1 : ((qd * 4 + 2 < p.num_tiles) ? 2 : 1); };   // slots with a tile in at least one CTA
 
     if (warp == kProducerWarp) {
         // ===================== weight producer: this CTA's half of every chunk =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, bphase = 0;
             for (int qd = cluster_id; qd < quads; qd += num_clusters) {
-                const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;   // slots with a tile in at least one CTA
-                for (int j = 0; j < kNumJobs; ++j) {
+                const int nslots = slots_of(qd);
+                for (int j = 0; j < kJobs; ++j) {
                     {   // this CTA's share of the layer's bias tile (single buffer, released by the last slot's bias MMA)
                         const uint32_t bbytes = j < 9 ? 2048u : (j == 9 ? 1024u : 128u);
                         mbar_wait(bias_empty, bphase ^ 1);
@@ -773,6 +532,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                             mbar_expect_tx(ring_full(stage), bytes);
                             bulk_g2s(sbase + kSmemRing + stage * kStageBytes, p.wimg + gofs, bytes, ring_full(stage));
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            if (kSplit) {      // the same chunk of the lo image goes into the next stage
+                                mbar_wait(ring_empty(stage), phase ^ 1);
+                                mbar_expect_tx(ring_full(stage), bytes);
+                                bulk_g2s(sbase + kSmemRing + stage * kStageBytes, p.wimg_lo + gofs, bytes, ring_full(stage));
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            }
                         }
                 }
             }
@@ -783,13 +548,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
             uint32_t stage = 0, phase = 0, bphase = 0;
             const uint32_t bias_full_leader = mapa(bias_full, 0);
             for (int qd = cluster_id; qd < quads; qd += num_clusters) {
-                const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;
-                for (int j = 0; j < kNumJobs; ++j) {
+                const int nslots = slots_of(qd);
+                for (int j = 0; j < kJobs; ++j) {
                     mbar_wait(bias_full, bphase);
                     mbar_arrive_cluster(bias_full_leader);
                     bphase ^= 1;
                     const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
-                    const int loads = ((KC <= kStages) ? 1 : nslots) * KC;
+                    const int loads = ((KC <= kStages) ? 1 : nslots) * KC * (kSplit ? 2 : 1);
                     for (int c = 0; c < loads; ++c) {
                         mbar_wait(ring_full(stage), phase);
                         mbar_arrive_cluster(mapa(ring_full(stage), 0));
@@ -811,13 +576,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
             const uint64_t biast_desc = (uint64_t)(((sbase + kSmemBiasTile) >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
             for (int qd = cluster_id; qd < quads; qd += num_clusters) {
 #pragma unroll 1
-                for (int j = 0; j < kNumJobs; ++j) {
+                for (int j = 0; j < kJobs; ++j) {
                     const int KC = (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4;
                     const int enc_kc = (j == 0) ? 0 : (j == 5 || j == 9) ? 4 : -1;
                     const bool enc_short = (j == 9);
                     const uint32_t idesc = (j < 9) ? id256 : (j == 9) ? id128 : id16;
                     const bool shared_w = KC <= kStages;                     // weights loaded once for both slots
-                    const int nslots = (qd * 4 + 2 < p.num_tiles) ? 2 : 1;
+                    const int nslots = slots_of(qd);
                     const uint32_t stage0 = stage, phase0 = phase;
 #pragma unroll 1
                     for (int t = 0; t < nslots; ++t) {
@@ -849,17 +614,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
                                     umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
                                     umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
                                 }
+                                if (kSplit) {
+                                    // lo(A) . hi(W): slot 1's buffers hold the lo parts of this tile; then hi(A) . lo(W)
+                                    // from the next stage (the split launch never sees the short enc_dir chunk)
+                                    const uint32_t l_lo = is_enc ? enc_lo + (uint32_t)(kEncBytes >> 4) : a_lo + (uint32_t)(kActBytes >> 4);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_f16_pair(d, umma_desc_from_lo(l_lo + 2 * k), umma_desc_from_lo(b_lo + 2 * k), idesc, 1u);
+                                    umma_commit_pair(ring_empty(st));
+                                    if (++st == kStages) { st = 0; ph ^= 1; }
+                                    mbar_wait_cluster(ring_full(st), ph);
+                                    tc_fence_after();
+                                    const uint32_t b2_lo = ring_lo + st * (kStageBytes >> 4);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_f16_pair(d, umma_desc_from_lo(a_lo + 2 * k), umma_desc_from_lo(b2_lo + 2 * k), idesc, 1u);
+                                }
                                 if (last_user) umma_commit_pair(ring_empty(st));
                                 if (kc == KC - 1) umma_commit_pair(acc_full(t));
                                 if (++st == kStages) { st = 0; ph ^= 1; }
                             }
                         }
                         __syncwarp();
-                        // every lane advances the ring position by KC stages
-                        phase ^= ((stage + (uint32_t)KC) / kStages) & 1u;
-                        stage = (stage + (uint32_t)KC) % kStages;
+                        // every lane advances the ring position by KC stages (2 KC in the split instantiation)
+                        const uint32_t used = (uint32_t)KC * (kSplit ? 2u : 1u);
+                        phase ^= ((stage + used) / kStages) & 1u;
+                        stage = (stage + used) % kStages;
                     }
                 }
+            }
+        }
+    } else if (kSplit) {
+        // ===================== split instantiation: warps 0-3 are the epilogue of the CTA's one tile ==========
+        if (warp < 4) {
+            const int q = warp & 3, row = q * 32 + lane;
+            uint8_t* act_hi = smem + kSmemAct;
+            uint8_t* act_lo = smem + kSmemAct + kActBytes;
+            uint8_t* enc_hi = smem + kSmemEnc;
+            uint8_t* enc_lo = smem + kSmemEnc + kEncBytes;
+            const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t act_ready_leader = mapa(act_ready(0), 0);
+            uint32_t acc_phase = 0;
+            const float4* ws4 = reinterpret_cast<const float4*>(p.heads + HeadOffsets::wsigma);
+            const float bsig = __ldg(p.heads + HeadOffsets::bsigma);
+            RowCtx cur, nxt;
+            auto tile_of = [&](int qd) { return qd * 2 + (int)rank; };
+            int qd = cluster_id;
+            if (qd < quads) prep_tile<kHalf, true>(p, tile_of(qd), row, enc_hi, cur, enc_lo);
+            for (; qd < quads; qd += num_clusters) {
+                float sig_acc = 0.f;
+#pragma unroll 1
+                for (int j = 0; j < kJobs; ++j) {
+                    named_bar_sync(1, kTileRows);
+                    if (row == 0) mbar_arrive_cluster(act_ready_leader);
+                    mbar_wait(acc_full(0), acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                    if (j == 7) epilogue_cols_split<kHalf, true>(tmem_row, act_hi, act_lo, row, ws4, &sig_acc);
+                    else epilogue_cols_split<kHalf, false>(tmem_row, act_hi, act_lo, row, ws4, &sig_acc);
+                    if (j == 7) {
+                        const float sg = fmaxf(sig_acc + bsig, 0.f);
+                        if (cur.valid) {
+                            p.sigma[cur.grow] = sg;
+                            if (p.stash)     // training forward: the ReLU gate of the sigma head reads the stashed output
+                                reinterpret_cast<float*>(p.stash + (size_t)(cur.grow >> 7) * kStashTileBytes + kStashOutOfs)[3 * 128 + (int)(cur.grow & 127)] = sg;
+                        }
+                        // dense_5 was the last reader of enc_xyz: the next tile's encoding can go in now
+                        const int nq = qd + num_clusters;
+                        if (nq < quads) prep_tile<kHalf, true>(p, tile_of(nq), row, enc_hi, nxt, enc_lo);
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                }
+                cur = nxt;
             }
         }
     } else if (warp < 8) {
@@ -888,12 +715,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
             const bool real_tile = tile_of(qd) < p.num_tiles;
             uint8_t* tstash = (kTrain && real_tile) ? p.stash + (size_t)tile_of(qd) * kStashTileBytes : nullptr;
             float sig_acc = 0.f;
-            for (int j = 0; j < kNumJobs; ++j) {
+            for (int j = 0; j < kJobs; ++j) {
                 // job boundary: everything the previous step wrote (encoding / activations) is complete and fenced
                 named_bar_sync(1 + t, kTileRows);
                 if (row == 0) mbar_arrive_cluster(act_ready_leader);      // this CTA's operand for job j is ready
                 bool issued = false;
-                // debug instantiation only (NERFB200_TC_DEBUG=3/4/5): drop the stash stores / the bitmask stores / both,
+                // debug instantiation only (NERFB200_OPT_DEBUG modes 3/4/5): drop the stash stores / the bitmask stores / both,
                 // to attribute the training forward's slowdown over the inference forward (tools/fwd_train_bench.py)
                 const bool no_stash_store = kDbg && (p.dbg_mode == 3 || p.dbg_mode == 5);
                 const bool no_mask_store = kDbg && (p.dbg_mode == 4 || p.dbg_mode == 5);
@@ -989,328 +816,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_
 }
 
 
-// =============================================================================================
-// v3: chunk-pipelined 2-CTA kernel (inference). One 128-row tile per CTA (256 rows per cluster), TWO
-// accumulator buffers in TMEM that alternate by layer, EIGHT epilogue warps (two per TMEM lane quadrant,
-// each pair splitting the columns) and one "activation chunk ready" barrier per 64 columns: the MMAs of
-// layer l+1 on K chunk c are issued as soon as the epilogue of layer l has produced columns [64c, 64c+64),
-// so the tensor core works on layer l+1 while layer l is still being drained -- the overlap comes from
-// the layer's own K loop instead of from a second tile, which frees shared memory for an 8-deep weight ring.
-constexpr int k3Stages = 8;
-constexpr int k3SmemAct = 0;                                   // 64 KB
-constexpr int k3SmemEnc = k3SmemAct + kActBytes;               // 16 KB
-constexpr int k3SmemRing = k3SmemEnc + kEncBytes;              // 8 x 16 KB
-constexpr int k3SmemBar = k3SmemRing + k3Stages * kStageBytes;
-constexpr int k3SmemBias = k3SmemBar + 256;                    // all biases + sigma head of the model (fp32)
-constexpr int k3SmemSig = k3SmemBias + ((HeadOffsets::total * 4 + 15) / 16) * 16;
-constexpr int k3SmemTotal = k3SmemSig + 128 * 4;
-static_assert(k3SmemTotal <= 232448, "exceeds the 227 KB dynamic shared memory limit");
-
-// encoding of one half (32 features) of the 64-column enc_xyz row: half 0 = [x,y,z, pairs 0..13, sin 14],
-// half 1 = [cos 14, pairs 15..29, 0]; pair p = (d = p / 10, l = p % 10) -> sin, cos of x_d * 2^l * pi
-template <bool kHalf>
-__device__ __forceinline__ void write_enc_xyz_half(const float (&xyz)[3], int half, uint8_t* enc, int row) {
-    float e[32];
-    if (half == 0) {
-        e[0] = xyz[0]; e[1] = xyz[1]; e[2] = xyz[2];
-#pragma unroll
-        for (int pp = 0; pp < 15; ++pp) {
-            const int d = pp / 10, l = pp % 10;
-            float sn, cs;
-            sincosf(__fmul_rn(xyz[d], __fmul_rn((float)(1 << l), 3.14159274101257324f)), &sn, &cs);
-            e[3 + 2 * pp] = sn;
-            if (pp < 14) e[4 + 2 * pp] = cs;
-        }
-    } else {
-#pragma unroll
-        for (int pp = 14; pp < 30; ++pp) {
-            const int d = pp / 10, l = pp % 10;
-            float sn, cs;
-            sincosf(__fmul_rn(xyz[d], __fmul_rn((float)(1 << l), 3.14159274101257324f)), &sn, &cs);
-            if (pp > 14) e[2 * pp - 29] = sn;
-            e[2 * pp - 28] = cs;
-        }
-        e[31] = 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        uint4 v;
-        v.x = pack2<kHalf>(e[8 * u + 0], e[8 * u + 1]);
-        v.y = pack2<kHalf>(e[8 * u + 2], e[8 * u + 3]);
-        v.z = pack2<kHalf>(e[8 * u + 4], e[8 * u + 5]);
-        v.w = pack2<kHalf>(e[8 * u + 6], e[8 * u + 7]);
-        *reinterpret_cast<uint4*>(enc + swz(row, half * 4 + u)) = v;
-    }
-}
-
-// one 64-column activation chunk (two groups of 32 accumulator columns) of this thread's row
-template <bool kHalf, bool kRelu, bool kSigma>
-__device__ __forceinline__ void v3_drain_chunk(uint32_t tmem_cols, const float* bias, uint8_t* chunk, int row, const float* wsig,
-                                               float& sig_acc) {
-    uint32_t r[2][32];
-    tmem_ld32(tmem_cols, r[0]);
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        uint32_t (&rr)[32] = r[g];
-        tmem_ld_wait(rr);
-        if (g == 0) tmem_ld32(tmem_cols + 32u, r[1]);
-        const float4* b4 = reinterpret_cast<const float4*>(bias + 32 * g);
-        uint32_t o[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 bb = b4[i];
-            float2 s0 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 0]), __uint_as_float(rr[4 * i + 1])), make_float2(bb.x, bb.y));
-            float2 s1 = __fadd2_rn(make_float2(__uint_as_float(rr[4 * i + 2]), __uint_as_float(rr[4 * i + 3])), make_float2(bb.z, bb.w));
-            if (kSigma) {   // sigma head on the fp32 activations (core/model.py:375)
-                const float4 w = reinterpret_cast<const float4*>(wsig + 32 * g)[i];
-                sig_acc = fmaf(fmaxf(s0.x, 0.f), w.x, sig_acc);
-                sig_acc = fmaf(fmaxf(s0.y, 0.f), w.y, sig_acc);
-                sig_acc = fmaf(fmaxf(s1.x, 0.f), w.z, sig_acc);
-                sig_acc = fmaf(fmaxf(s1.y, 0.f), w.w, sig_acc);
-            }
-            if (kRelu) { o[2 * i] = pack2_relu<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2_relu<kHalf>(s1.x, s1.y); }
-            else { o[2 * i] = pack2<kHalf>(s0.x, s0.y); o[2 * i + 1] = pack2<kHalf>(s1.x, s1.y); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<uint4*>(chunk + swz(row, g * 4 + u)) = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
-    }
-}
-
-template <bool kHalf>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) mlp_tc_forward_v3_kernel(const TcParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const uint32_t sbase = smem_u32(smem);
-    const uint32_t sbar = sbase + k3SmemBar;
-    const bool dbg_on = p.dbg != nullptr && blockIdx.x < 2;
-    unsigned long long dbg_acc0 = 0, dbg_acc1 = 0, dbg_acc2 = 0, dbg_acc3 = 0;
-    const long long t_kernel0 = clock64();
-    auto ring_full = [&](int s) { return sbar + 8 * s; };
-    auto ring_empty = [&](int s) { return sbar + 8 * (k3Stages + s); };
-    auto chunk_ready = [&](int c) { return sbar + 8 * (2 * k3Stages + c); };      // leader: 4 warps x 2 CTAs
-    const uint32_t enc_ready = sbar + 8 * (2 * k3Stages + 4);                     // leader: 8 warps x 2 CTAs
-    auto acc_full = [&](int b) { return sbar + 8 * (2 * k3Stages + 5 + b); };     // both CTAs (multicast commit)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + k3SmemBar + 8 * (2 * k3Stages + 7));
-    float* s_heads = reinterpret_cast<float*>(smem + k3SmemBias);
-    float* s_sig = reinterpret_cast<float*>(smem + k3SmemSig);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < k3Stages; ++s) { mbar_init(ring_full(s), rank == 0 ? 2 : 1); mbar_init(ring_empty(s), 1); }
-        for (int c = 0; c < 4; ++c) mbar_init(chunk_ready(c), 8);
-        mbar_init(enc_ready, 16);
-        mbar_init(acc_full(0), 1); mbar_init(acc_full(1), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = threadIdx.x; i < HeadOffsets::total; i += kThreads) s_heads[i] = __ldg(p.heads + i);
-    cluster_sync_all();
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const int num_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
-    const int tpairs = (p.num_tiles + 1) >> 1;          // a cluster works on 2 tiles at a time (one per CTA)
-    constexpr int fmt = kHalf ? 0 : 1;
-
-    // chunk list of job j in ISSUE order: the chunk fed from the encoding buffer goes first (it is ready long
-    // before the activations), then the activation chunks 0..3. kc_of(j, i) = K-chunk index in the packed image.
-    auto n_chunks = [](int j) { return (j == 0) ? 1 : (j == 5 || j == 9) ? 5 : (j == 10) ? 2 : 4; };
-    auto kc_of = [](int j, int i) { return (j == 5 || j == 9) ? (i == 0 ? 4 : i - 1) : i; };
-
-    if (warp == kProducerWarp) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int tp = cluster_id; tp < tpairs; tp += num_clusters)
-                for (int j = 0; j < kNumJobs; ++j) {
-                    const int cb = c_job_begin[j], NC = n_chunks(j);
-                    for (int i = 0; i < NC; ++i) {
-                        const int kc = kc_of(j, i);
-                        uint32_t gofs, bytes;
-                        if (j < 9) { gofs = c_chunks[cb + (int)rank * NC + kc].gofs; bytes = 16384; }
-                        else if (j == 9) { gofs = c_chunks[cb + kc].gofs + rank * 8192u; bytes = 8192; }
-                        else { gofs = c_chunks[cb + kc].gofs + rank * 1024u; bytes = 1024; }
-                        mbar_wait(ring_empty(stage), phase ^ 1);
-                        mbar_expect_tx(ring_full(stage), bytes);
-                        bulk_g2s(sbase + k3SmemRing + stage * kStageBytes, p.wimg + gofs, bytes, ring_full(stage));
-                        if (++stage == k3Stages) { stage = 0; phase ^= 1; }
-                    }
-                }
-        }
-    } else if (warp == kMmaWarp) {
-        if (lane == 0 && rank == 1) {
-            uint32_t stage = 0, phase = 0;
-            for (int tp = cluster_id; tp < tpairs; tp += num_clusters)
-                for (int j = 0; j < kNumJobs; ++j)
-                    for (int i = 0; i < n_chunks(j); ++i) {
-                        mbar_wait(ring_full(stage), phase);
-                        mbar_arrive_cluster(mapa(ring_full(stage), 0));
-                        if (++stage == k3Stages) { stage = 0; phase ^= 1; }
-                    }
-        } else if (lane == 0) {
-            const uint32_t ring_lo = ((sbase + k3SmemRing) >> 4) & 0x3FFFu;
-            const uint32_t act_lo = ((sbase + k3SmemAct) >> 4) & 0x3FFFu, enc_lo = ((sbase + k3SmemEnc) >> 4) & 0x3FFFu;
-            constexpr uint32_t id256 = umma_idesc_pair(fmt, 256), id128 = umma_idesc_pair(fmt, 128), id16 = umma_idesc_pair(fmt, 16);
-            uint32_t stage = 0, phase = 0, chunk_phase_bits = 0, enc_phase = 0;
-            for (int tp = cluster_id; tp < tpairs; tp += num_clusters) {
-#pragma unroll 1
-                for (int j = 0; j < kNumJobs; ++j) {
-                    const int NC = n_chunks(j);
-                    const bool has_enc = (j == 0 || j == 5 || j == 9);
-                    const uint32_t idesc = (j < 9) ? id256 : (j == 9) ? id128 : id16;
-                    const uint32_t d = tmem_base + (uint32_t)(((j == 10) ? 1 : (j & 1)) * 256);
-                    if (j == 0 || j == 9) { NB_T0(); mbar_wait_cluster(enc_ready, enc_phase); NB_T1(2); enc_phase ^= 1; tc_fence_after(); }
-#pragma unroll 1
-                    for (int i = 0; i < NC; ++i) {
-                        const bool is_enc = has_enc && i == 0;
-                        uint32_t a_lo;
-                        if (is_enc) a_lo = enc_lo;
-                        else {
-                            const int ac = has_enc && j != 0 ? i - 1 : i;            // activation chunk index
-                            { NB_T0(); mbar_wait_cluster(chunk_ready(ac), (chunk_phase_bits >> ac) & 1u); NB_T1(0); }
-                            chunk_phase_bits ^= 1u << ac;
-                            a_lo = act_lo + (uint32_t)(ac * 1024);
-                        }
-                        { NB_T0(); mbar_wait_cluster(ring_full(stage), phase); NB_T1(1); }
-                        tc_fence_after();
-                        const uint32_t b_lo = ring_lo + stage * (kStageBytes >> 4);
-                        umma_f16_pair(d, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, i == 0 ? 0u : 1u);
-                        umma_f16_pair(d, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
-                        if (!(is_enc && j == 9)) {      // enc_dir is 32 columns: 2 K-steps
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
-                            umma_f16_pair(d, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
-                        }
-                        umma_commit_pair(ring_empty(stage));
-                        if (++stage == k3Stages) { stage = 0; phase ^= 1; }
-                    }
-                    umma_commit_pair(acc_full((j == 10) ? 1 : (j & 1)));
-                }
-            }
-        }
-    } else {
-        // ===================== 8 epilogue warps: group = warp >> 2 splits the columns, warp & 3 = TMEM lane quadrant
-        const int grp = warp >> 2, q = warp & 3, row = q * 32 + lane;
-        uint8_t* act = smem + k3SmemAct;
-        uint8_t* enc = smem + k3SmemEnc;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t enc_ready_leader = mapa(enc_ready, 0);
-        uint32_t acc_phase_bits = 0;
-        const float* wsig = s_heads + HeadOffsets::wsigma;
-
-        auto load_row = [&](int tile, RowCtx& rc, float (&xyz)[3]) {
-            rc.grow = (int64_t)tile * kTileRows + row;
-            rc.valid = tile < p.num_tiles && rc.grow < p.R;
-            const int64_t lrow = rc.valid ? rc.grow : p.R - 1;
-            const int64_t ray = lrow / p.S;
-            const float tv = __ldg(p.t + lrow);
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                rc.dir[d] = __ldg(p.rd + 3 * ray + d);
-                xyz[d] = __fadd_rn(__ldg(p.ro + 3 * ray + d), __fmul_rn(tv, rc.dir[d]));
-            }
-        };
-        auto signal = [&](uint32_t cluster_bar) {      // this warp's share of an operand is written: publish it
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(cluster_bar);
-        };
-
-        RowCtx cur, nxt;
-        int tp = cluster_id;
-        if (tp < tpairs) {
-            float xyz[3];
-            load_row(tp * 2 + (int)rank, cur, xyz);
-            write_enc_xyz_half<kHalf>(xyz, grp, enc, row);
-            signal(enc_ready_leader);
-        }
-        for (; tp < tpairs; tp += num_clusters) {
-            float sig_acc = 0.f;
-#pragma unroll 1
-            for (int j = 0; j < kNumJobs; ++j) {
-                const int buf = (j == 10) ? 1 : (j & 1);
-                { NB_T0(); mbar_wait(acc_full(buf), (acc_phase_bits >> buf) & 1u); NB_T1(0); }
-                acc_phase_bits ^= 1u << buf;
-                tc_fence_after();
-                long long _te = dbg_on ? clock64() : 0;
-                const uint32_t tcols = tmem_lane + (uint32_t)(buf * 256);
-                const float* bias = s_heads + HeadOffsets::bias(j);
-                if (j < 9) {
-                    // N = 256: this group drains columns [128 grp, 128 grp + 128) = activation chunks 2 grp, 2 grp + 1
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int ch = grp * 2 + c;
-                        if (j == 7) v3_drain_chunk<kHalf, true, true>(tcols + 64u * ch, bias + 64 * ch, act + ch * 16384, row, wsig + 64 * ch, sig_acc);
-                        else if (j == 8) v3_drain_chunk<kHalf, false, false>(tcols + 64u * ch, bias + 64 * ch, act + ch * 16384, row, wsig, sig_acc);
-                        else v3_drain_chunk<kHalf, true, false>(tcols + 64u * ch, bias + 64 * ch, act + ch * 16384, row, wsig, sig_acc);
-                        signal(mapa(chunk_ready(ch), 0));
-                    }
-                    if (j == 5) {
-                        // dense_5 has consumed enc_xyz: the encoding buffer now takes enc_dir (32 features) + zeros
-                        if (grp == 0) {
-                            write_enc_dir<kHalf>(cur.dir, enc, row);          // writes all 8 units (4..7 = 0)
-                        }
-                        signal(enc_ready_leader);
-                    }
-                    if (j == 7) {
-                        if (grp == 1) s_sig[row] = sig_acc;
-                        named_bar_sync(1, 256);
-                        if (grp == 0 && cur.valid) p.sigma[cur.grow] = fmaxf(sig_acc + s_sig[row] + s_heads[HeadOffsets::bsigma], 0.f);
-                    }
-                } else if (j == 9) {
-                    // N = 128: group g drains columns [64 g, 64 g + 64) = activation chunk g
-                    v3_drain_chunk<kHalf, true, false>(tcols + 64u * grp, bias + 64 * grp, act + grp * 16384, row, wsig, sig_acc);
-                    signal(mapa(chunk_ready(grp), 0));
-                    // dense_9 has consumed enc_dir: encode the next tile now
-                    const int ntp = tp + num_clusters;
-                    if (ntp < tpairs) {
-                        float xyz[3];
-                        load_row(ntp * 2 + (int)rank, nxt, xyz);
-                        write_enc_xyz_half<kHalf>(xyz, grp, enc, row);
-                        signal(enc_ready_leader);
-                    }
-                } else {
-                    if (grp == 0) {
-                        uint32_t r[32];
-                        tmem_ld32(tcols, r);
-                        tmem_ld_wait(r);
-                        if (cur.valid) {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const float x = __uint_as_float(r[c]) + bias[c];
-                                p.rgb[3 * cur.grow + c] = 1.f / (1.f + expf(-x));
-                            }
-                        }
-                    }
-                    tc_fence_before();
-                }
-                if (dbg_on) dbg_acc1 += (unsigned long long)(clock64() - _te);
-            }
-            cur = nxt;
-        }
-    }
-    if (dbg_on && lane == 0 && (warp == kProducerWarp || warp == kMmaWarp || warp == 0 || warp == 4)) {
-        int rowi = (warp == kProducerWarp ? 0 : warp == kMmaWarp ? 1 : warp == 0 ? 2 : 3);
-        unsigned long long* o = p.dbg + blockIdx.x * 32 + rowi * 8;
-        o[0] = dbg_acc0; o[1] = dbg_acc1; o[2] = dbg_acc2; o[3] = dbg_acc3; o[4] = (unsigned long long)(clock64() - t_kernel0);
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-}
 
 // ---------------------------------------------------------------------------------------------
-static bool g_table_uploaded = false;
+// __constant__ memory is per device: the tables are uploaded by every tc_create, on the context's device.
 static int upload_table() {
-    if (g_table_uploaded) return 0;
     const ChunkTable& t = chunk_table();
     NB_CUDA(cudaMemcpyToSymbol(c_chunks, t.c, sizeof(Chunk) * kMaxChunks));
     NB_CUDA(cudaMemcpyToSymbol(c_job_begin, t.job_begin, sizeof(int) * (kNumJobs + 1)));
-    g_table_uploaded = true;
+    return 0;
+}
+
+int check_device(const nerfb200_ctx* ctx, const char* fn) {
+    int dev = -1;
+    NB_CUDA(cudaGetDevice(&dev));
+    NB_CHECK_ARG(dev == ctx->device, "%s: the context was created on device %d but the current device is %d", fn, ctx->device, dev);
+    return 0;
+}
+
+template <bool H, bool T, bool D, bool S> static int set_smem_attr() {
+    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<H, T, D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     return 0;
 }
 
@@ -1318,115 +842,151 @@ int tc_create(nerfb200_ctx* ctx) {
     NB_CUDA(cudaGetDevice(&ctx->device));
     NB_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
     const ChunkTable& t = chunk_table();
-    ctx->replicas = kDefaultReplicas;
-    if (const char* e = getenv("NERFB200_WEIGHT_REPLICAS")) {
-        int r = atoi(e);
-        if (r >= 1 && r <= kMaxReplicas) ctx->replicas = r;
-    }
     for (int pz = 0; pz < 2; ++pz)
-        for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc(&ctx->packed[pz][m], (size_t)t.bytes * ctx->replicas));
+        for (int m = 0; m < 2; ++m) {
+            NB_CUDA(cudaMalloc(&ctx->packed[pz][m], (size_t)t.bytes));
+            NB_CUDA(cudaMalloc(&ctx->packed_lo[pz][m], (size_t)t.bias_ofs));
+        }
     for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc((void**)&ctx->head_params[m], HeadOffsets::total * sizeof(float)));
     int rc = upload_table();
     if (rc) return rc;
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_pair_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(mlp_tc_forward_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3SmemTotal));
+    if ((rc = set_smem_attr<false, false, false, false>())) return rc;
+    if ((rc = set_smem_attr<true, false, false, false>())) return rc;
+    if ((rc = set_smem_attr<false, true, false, false>())) return rc;
+    if ((rc = set_smem_attr<true, true, false, false>())) return rc;
+    if ((rc = set_smem_attr<false, false, true, false>())) return rc;
+    if ((rc = set_smem_attr<true, false, true, false>())) return rc;
+    if ((rc = set_smem_attr<false, true, true, false>())) return rc;
+    if ((rc = set_smem_attr<true, true, true, false>())) return rc;
+    if ((rc = set_smem_attr<false, false, false, true>())) return rc;
+    if ((rc = set_smem_attr<true, false, false, true>())) return rc;
+    if ((rc = tf32_create(ctx))) return rc;
     return tc_train_create(ctx);
 }
 
 void tc_destroy(nerfb200_ctx* ctx) {
     tc_train_destroy(ctx);
+    tf32_destroy(ctx);
     for (int pz = 0; pz < 2; ++pz)
-        for (int m = 0; m < 2; ++m) if (ctx->packed[pz][m]) cudaFree(ctx->packed[pz][m]);
+        for (int m = 0; m < 2; ++m) {
+            if (ctx->packed[pz][m]) cudaFree(ctx->packed[pz][m]);
+            if (ctx->packed_lo[pz][m]) cudaFree(ctx->packed_lo[pz][m]);
+        }
     for (int m = 0; m < 2; ++m) if (ctx->head_params[m]) cudaFree(ctx->head_params[m]);
 }
 
+// Packs the operand images of the precisions in ctx->pack_mask (bit 0 bf16, bit 1 fp16, bit 2 tf32; a training loop
+// that uses one precision sets the mask and saves the other images' launches every step).
 int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st) {
+    int rc = check_device(ctx, "pack_weights");
+    if (rc) return rc;
     const ChunkTable& t = chunk_table();
-    int64_t units = t.bias_ofs / 16;
+    const int64_t units = t.bias_ofs / 16;
+    const unsigned grid = (unsigned)((units + 255) / 256), bgrid = (kNumJobs * 256 + 255) / 256;
     for (int m = 0; m < 2; ++m) {
         const float* P = flat_params + (int64_t)m * kParamsPerModel;
-        pack_weights_kernel<__nv_bfloat16><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m], t.n);
-        pack_weights_kernel<__half><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m], t.n);
-        for (int pz = 0; pz < 2; ++pz)
-            for (int r = 1; r < ctx->replicas; ++r)
-                NB_CUDA(cudaMemcpyAsync((uint8_t*)ctx->packed[pz][m] + (size_t)r * t.bytes, ctx->packed[pz][m], t.bytes,
-                                        cudaMemcpyDeviceToDevice, st));
-        pack_bias_tiles_kernel<__nv_bfloat16><<<(kNumJobs * 256 + 255) / 256, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m] + t.bias_ofs);
-        pack_bias_tiles_kernel<__half><<<(kNumJobs * 256 + 255) / 256, 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m] + t.bias_ofs);
+        if (ctx->pack_mask & 1) {
+            pack_weights_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m], t.n);
+            NB_LAUNCH_CHECK();
+            pack_bias_tiles_kernel<__nv_bfloat16><<<bgrid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m] + t.bias_ofs);
+            NB_LAUNCH_CHECK();
+        }
+        if (ctx->pack_mask & 2) {
+            pack_weights_kernel<__half, false><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m], t.n);
+            NB_LAUNCH_CHECK();
+            pack_bias_tiles_kernel<__half><<<bgrid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m] + t.bias_ofs);
+            NB_LAUNCH_CHECK();
+        }
+        if (ctx->precise_last) {   // lo images of the split launch (tf32 renders use the bf16 pair)
+            if (ctx->pack_mask & 5) { pack_weights_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed_lo[0][m], t.n); NB_LAUNCH_CHECK(); }
+            if (ctx->pack_mask & 2) { pack_weights_kernel<__half, true><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed_lo[1][m], t.n); NB_LAUNCH_CHECK(); }
+            if ((ctx->pack_mask & 5) == 4) {   // tf32 only: the split launch still needs the bf16 hi image
+                pack_weights_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m], t.n);
+                NB_LAUNCH_CHECK();
+                pack_bias_tiles_kernel<__nv_bfloat16><<<bgrid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m] + t.bias_ofs);
+                NB_LAUNCH_CHECK();
+            }
+        }
         pack_heads_kernel<<<(HeadOffsets::total + 255) / 256, 256, 0, st>>>(P, ctx->head_params[m]);
+        NB_LAUNCH_CHECK();
     }
-    NB_LAUNCH_CHECK();
-    int rc = tc_train_pack(ctx, flat_params, st);
+    if (ctx->pack_mask & 4) { rc = tf32_pack(ctx, flat_params, st); if (rc) return rc; }
+    rc = tc_train_pack(ctx, flat_params, st);
     if (rc) return rc;
     ctx->packed_valid = true;
+    ctx->packed_mask = ctx->pack_mask;
+    ctx->packed_precise = ctx->precise_last;
     return 0;
+}
+
+// The second, small launch of a forward: sigma of the last sample of every ray with split operands (see the kernel).
+static int launch_split(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
+                        float* sigma, void* stash, cudaStream_t st) {
+    TcParams p{};
+    p.wimg = (const uint8_t*)ctx->packed[half ? 1 : 0][which];
+    p.wimg_lo = (const uint8_t*)ctx->packed_lo[half ? 1 : 0][which];
+    p.bias_ofs = chunk_table().bias_ofs;
+    p.last_only = 1;
+    p.heads = ctx->head_params[which];
+    p.ro = ro; p.rd = rd; p.t = t; p.rgb = nullptr; p.sigma = sigma; p.R = B; p.S = S;
+    p.stash = (uint8_t*)stash;
+    p.num_tiles = (int)((B + kTileRows - 1) / kTileRows);
+    const int units = (p.num_tiles + 1) / 2;
+    const int clusters = units < ctx->num_sms / 2 ? units : ctx->num_sms / 2;
+    if (half) mlp_tc_forward_pair_kernel<true, false, false, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+    else mlp_tc_forward_pair_kernel<false, false, false, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);
+    NB_LAUNCH_CHECK();
+    return 0;
+}
+
+int tc_precise_last(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
+                    float* sigma, void* stash, cudaStream_t st) {
+    if (!ctx->precise_last || S < 2 || B == 0) return 0;
+    if (!ctx->packed_precise || !(ctx->packed_mask & (half ? 2 : 5))) {
+        set_error("mlp_forward: the split images of this precision were not packed (option changed after pack_weights)");
+        return NERFB200_ESTATE;
+    }
+    return launch_split(ctx, which, half, B, S, ro, rd, t, sigma, stash, st);
 }
 
 int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* ro, const float* rd, const float* t,
                float* rgb, float* sigma, void* workspace, void* stash, cudaStream_t st) {
     (void)workspace;
-    if (!ctx->packed_valid) { set_error("mlp_forward: pack_weights has not been called"); return NERFB200_ESTATE; }
+    int rc = check_device(ctx, "mlp_forward");
+    if (rc) return rc;
+    if (!ctx->packed_valid || !(ctx->packed_mask & (half ? 2 : 1))) {
+        set_error("mlp_forward: pack_weights has not been called for this precision");
+        return NERFB200_ESTATE;
+    }
     const int64_t R = B * S;
     if (R == 0) return 0;
     NB_CHECK_ARG((R + kTileRows - 1) / kTileRows < (int64_t)1 << 30, "mlp_forward: too many rows");
-    TcParams p;
+    TcParams p{};
     p.wimg = (const uint8_t*)ctx->packed[half ? 1 : 0][which];
-    p.wimg_stride = chunk_table().bytes;
     p.bias_ofs = chunk_table().bias_ofs;
-    p.replicas = ctx->replicas;
     p.heads = ctx->head_params[which];
     p.ro = ro; p.rd = rd; p.t = t; p.rgb = rgb; p.sigma = sigma; p.R = R; p.S = S;
     p.stash = (uint8_t*)stash;
     p.num_tiles = (int)((R + kTileRows - 1) / kTileRows);
-    int pairs = (p.num_tiles + 1) / 2;
-    int grid = pairs < ctx->num_sms ? pairs : ctx->num_sms;
-    static const bool debug = getenv("NERFB200_TC_DEBUG") != nullptr;
-    p.dbg = nullptr;
-    p.dbg_mode = debug ? atoi(getenv("NERFB200_TC_DEBUG")) : 0;
+    const bool debug = ctx->debug != 0;      // developer cycle counters (nerfb200_set_option NERFB200_OPT_DEBUG)
+    p.dbg_mode = ctx->debug;
     if (debug) {
         NB_CUDA(cudaMalloc((void**)&p.dbg, 128 * sizeof(unsigned long long)));
         NB_CUDA(cudaMemsetAsync(p.dbg, 0, 128 * sizeof(unsigned long long), st));
     }
-    static const bool use_pair = getenv("NERFB200_TC_PAIR") ? atoi(getenv("NERFB200_TC_PAIR")) != 0 : true;
-    static const bool use_v3 = getenv("NERFB200_TC_V3") ? atoi(getenv("NERFB200_TC_V3")) != 0 : false;
-    if (use_v3 && !stash) {
-        int tpairs = (p.num_tiles + 1) / 2;
-        int clusters = tpairs < ctx->num_sms / 2 ? tpairs : ctx->num_sms / 2;
-        if (half) mlp_tc_forward_v3_kernel<true><<<2 * clusters, kThreads, k3SmemTotal, st>>>(p);
-        else mlp_tc_forward_v3_kernel<false><<<2 * clusters, kThreads, k3SmemTotal, st>>>(p);
-    } else if (use_pair) {
-        int quads = (p.num_tiles + 3) / 4;
-        int clusters = quads < ctx->num_sms / 2 ? quads : ctx->num_sms / 2;
+    const int quads = (p.num_tiles + 3) / 4;
+    const int clusters = quads < ctx->num_sms / 2 ? quads : ctx->num_sms / 2;
 #define NB_LAUNCH_PAIR(H, T)                                                                                   \
     do {                                                                                                       \
         if (debug) mlp_tc_forward_pair_kernel<H, T, true><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);      \
         else mlp_tc_forward_pair_kernel<H, T, false><<<2 * clusters, kThreads, kSmemTotal, st>>>(p);           \
     } while (0)
-        if (stash) {
-            if (half) NB_LAUNCH_PAIR(true, true); else NB_LAUNCH_PAIR(false, true);
-        } else {
-            if (half) NB_LAUNCH_PAIR(true, false); else NB_LAUNCH_PAIR(false, false);
-        }
-#undef NB_LAUNCH_PAIR
-    } else if (stash) {
-        if (half) mlp_tc_forward_kernel<true, true><<<grid, kThreads, kSmemTotal, st>>>(p);
-        else mlp_tc_forward_kernel<false, true><<<grid, kThreads, kSmemTotal, st>>>(p);
+    if (stash) {
+        if (half) NB_LAUNCH_PAIR(true, true); else NB_LAUNCH_PAIR(false, true);
     } else {
-        if (half) mlp_tc_forward_kernel<true, false><<<grid, kThreads, kSmemTotal, st>>>(p);
-        else mlp_tc_forward_kernel<false, false><<<grid, kThreads, kSmemTotal, st>>>(p);
+        if (half) NB_LAUNCH_PAIR(true, false); else NB_LAUNCH_PAIR(false, false);
     }
+#undef NB_LAUNCH_PAIR
     NB_LAUNCH_CHECK();
     if (debug) {
         unsigned long long h[128];
@@ -1434,12 +994,13 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
         NB_CUDA(cudaStreamSynchronize(st));
         cudaFree(p.dbg);
         const char* names[4] = {"producer", "mma", "epi0", "epi1"};
-        fprintf(stderr, "[tc debug] tiles=%d grid=%d (block 0 cycles)\n", p.num_tiles, grid);
+        fprintf(stderr, "[tc debug] tiles=%d clusters=%d (cluster 0 cycles)\n", p.num_tiles, clusters);
         for (int r = 0; r < 8; ++r)
             fprintf(stderr, "  cta%d %-8s wait0=%llu wait1/epi=%llu encdir=%llu prep=%llu total=%llu\n", r / 4, names[r % 4], h[r * 8],
                     h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
+        return 0;
     }
-    return 0;
+    return tc_precise_last(ctx, which, half, B, S, ro, rd, t, sigma, stash, st);
 }
 
 }  // namespace nb

@@ -2,7 +2,7 @@
 //
 // Three kernels per model and step, all tcgen05.mma with fp32 accumulation in TMEM and 16-bit operands:
 //
-//  1. bwd_data_kernel  -- per 128-row tile, the chain dZ_9 -> dZ_8 -> ... -> dZ_0 stays on chip like the
+//  1. bwd_data_pair_kernel -- per 128-row tile, the chain dZ_9 -> dZ_8 -> ... -> dZ_0 stays on chip like the
 //     forward: dX = dZ . W^T (W^T streamed through the bulk-TMA ring), the epilogue applies the ReLU
 //     bitmask stashed by the training forward and writes dZ_{l-1} as the next A operand. The rgb and
 //     sigma heads (N = 3 and 1) are fp32 CUDA-core work in the prologue/epilogue. Every dZ_l leaves as
@@ -96,7 +96,7 @@ constexpr int kBThreads = 320;
 constexpr int kBProducerWarp = 8, kBMmaWarp = 9;
 
 struct BwdParams {
-    const uint8_t* wimg; uint32_t wimg_stride; int replicas;
+    const uint8_t* wimg;
     const float* P;              // fp32 master parameters of this model (rgb / sigma heads)
     const uint8_t* stash;        // activation stash of the training forward
     uint8_t* gstash;             // out: gradient stash
@@ -150,214 +150,6 @@ __device__ __forceinline__ void bwd_epilogue_cols(uint32_t tmem_row, uint8_t* ac
         }
     }
 }
-
-template <bool kHalf>
-__global__ void __launch_bounds__(kBThreads, 1) bwd_data_kernel(const BwdParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t sbase = smem_u32(smem);
-    const uint32_t sbar = sbase + kBSmemBar;
-    // barriers: ring_full[4], ring_empty[4], act_ready[2], acc_full[2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kBSmemBar + 8 * (2 * kBStages + 4));
-    float* s_wsig = reinterpret_cast<float*>(smem + kBSmemWsig);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kBStages; ++s) { mbar_init(sbar + 8 * s, 1); mbar_init(sbar + 8 * (kBStages + s), 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(sbar + 8 * (2 * kBStages + t), kTileRows); mbar_init(sbar + 8 * (2 * kBStages + 2 + t), 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x < 256) s_wsig[threadIdx.x] = p.P[kernel_offset(LSIGMA) + threadIdx.x];
-    if (warp == kBMmaWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
-    const int pairs = (p.num_tiles + 1) >> 1;
-    constexpr int fmt = kHalf ? 0 : 1;
-
-    if (warp == kBProducerWarp) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint8_t* wimg = p.wimg + (size_t)(blockIdx.x % p.replicas) * p.wimg_stride;
-            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x)
-                for (int j = 0; j < kBwdJobs; ++j)
-                    for (int t = 0; t < 2; ++t) {
-                        if (pr * 2 + t >= p.num_tiles) continue;
-                        for (int ci = c_bwd_job_begin[j]; ci < c_bwd_job_begin[j + 1]; ++ci) {
-                            mbar_wait(sbar + 8 * (kBStages + stage), phase ^ 1);
-                            mbar_expect_tx(sbar + 8 * stage, kChunkBytes);
-                            bulk_g2s(sbase + kBSmemRing + stage * kChunkBytes, wimg + c_bwd_chunks[ci].gofs, kChunkBytes, sbar + 8 * stage);
-                            if (++stage == kBStages) { stage = 0; phase ^= 1; }
-                        }
-                    }
-        }
-    } else if (warp == kBMmaWarp) {
-        if (lane == 0) {
-            const uint32_t ring_lo = ((sbase + kBSmemRing) >> 4) & 0x3FFFu;
-            constexpr uint32_t idesc = umma_idesc(fmt, 128);
-            uint32_t stage = 0, phase = 0, act_phase_bits = 0;
-            for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
-#pragma unroll 1
-                for (int j = 0; j < kBwdJobs; ++j) {
-                    const int KC = j == 0 ? 2 : 4;
-#pragma unroll 1
-                    for (int t = 0; t < 2; ++t) {
-                        if (pr * 2 + t >= p.num_tiles) continue;
-                        mbar_wait(sbar + 8 * (2 * kBStages + t), (act_phase_bits >> t) & 1u);
-                        act_phase_bits ^= 1u << t;
-                        tc_fence_after();
-                        const uint32_t act_lo = ((sbase + kBSmemAct + t * 4 * kChunkBytes) >> 4) & 0x3FFFu;
-                        const uint32_t d = tmem_base + (uint32_t)(t * 256);
-#pragma unroll 1
-                        for (int nh = 0; nh < 2; ++nh) {
-                            const uint32_t dd = d + (uint32_t)(nh * 128);
-#pragma unroll 1
-                            for (int kc = 0; kc < KC; ++kc) {
-                                mbar_wait(sbar + 8 * stage, phase);
-                                tc_fence_after();
-                                const uint32_t a_lo = act_lo + (uint32_t)(kc * 1024);
-                                const uint32_t b_lo = ring_lo + stage * (kChunkBytes >> 4);
-                                umma_f16(dd, umma_desc_from_lo(a_lo), umma_desc_from_lo(b_lo), idesc, kc == 0 ? 0u : 1u);
-                                umma_f16(dd, umma_desc_from_lo(a_lo + 2), umma_desc_from_lo(b_lo + 2), idesc, 1u);
-                                umma_f16(dd, umma_desc_from_lo(a_lo + 4), umma_desc_from_lo(b_lo + 4), idesc, 1u);
-                                umma_f16(dd, umma_desc_from_lo(a_lo + 6), umma_desc_from_lo(b_lo + 6), idesc, 1u);
-                                umma_commit(sbar + 8 * (kBStages + stage));
-                                if (++stage == kBStages) { stage = 0; phase ^= 1; }
-                            }
-                        }
-                        umma_commit(sbar + 8 * (2 * kBStages + 2 + t));
-                    }
-                }
-            }
-        }
-    } else if (warp < 8) {
-        const int t = warp >> 2, q = warp & 3, row = q * 32 + lane;
-        uint8_t* act = smem + kBSmemAct + t * 4 * kChunkBytes;
-        uint8_t* head = smem + kBSmemHead + t * kChunkBytes;
-        const uint32_t act_saddr = sbase + kBSmemAct + t * 4 * kChunkBytes, head_saddr = sbase + kBSmemHead + t * kChunkBytes;
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256);
-        const uint32_t act_ready = sbar + 8 * (2 * kBStages + t), acc_full = sbar + 8 * (2 * kBStages + 2 + t);
-        uint32_t acc_phase = 0;
-        uint8_t* pend_dst = nullptr; uint32_t pend_bytes = 0; bool pend_head = false; uint8_t* pend_head_dst = nullptr;
-
-        for (int pr = blockIdx.x; pr < pairs; pr += gridDim.x) {
-            const int tile = pr * 2 + t;
-            if (tile >= p.num_tiles) continue;
-            const uint8_t* tstash = p.stash + (size_t)tile * kStashTileBytes;
-            uint8_t* gst = p.gstash + (size_t)tile * kGradTileBytes;
-            const int64_t grow = (int64_t)tile * kTileRows + row;
-            const bool valid = grow < p.R;
-            const float* outs = reinterpret_cast<const float*>(tstash + kStashOutOfs);
-
-            // ---- heads (fp32, CUDA cores): dZ_rgb = d_rgb * rgb(1-rgb); dZ_sigma = d_sigma * [sigma > 0]
-            float dzr[3] = {0.f, 0.f, 0.f}, dzs = 0.f;
-            if (valid) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float y = outs[3 * row + c];
-                    dzr[c] = __ldg(p.d_rgb + 3 * grow + c) * y * (1.f - y);
-                }
-                dzs = outs[3 * 128 + row] > 0.f ? __ldg(p.d_sigma + grow) : 0.f;
-            }
-            // ---- everything below runs at a job boundary: wait until the previous tile's stores have read smem
-            named_bar_sync(1 + t, kTileRows);
-            bool issued = false;
-            if (row == 0) {
-                if (pend_bytes) { bulk_s2g(pend_dst, act_saddr, pend_bytes); issued = true; }
-                if (pend_head) { bulk_s2g(pend_head_dst, head_saddr, kChunkBytes); issued = true; }
-                if (issued) { bulk_commit_group(); bulk_wait_read_all(); }
-            }
-            pend_bytes = 0; pend_head = false;
-            named_bar_sync(1 + t, kTileRows);
-            // head chunk image: cols 0..2 = dZ_rgb, col 3 = dZ_sigma, rest 0
-            {
-                uint4 o = make_uint4(pack2<kHalf>(dzr[0], dzr[1]), pack2<kHalf>(dzr[2], dzs), 0u, 0u);
-                *reinterpret_cast<uint4*>(head + swz(row, 0)) = o;
-#pragma unroll
-                for (int u = 1; u < 8; ++u) *reinterpret_cast<uint4*>(head + swz(row, u)) = make_uint4(0u, 0u, 0u, 0u);
-            }
-            // dZ_9 = (dZ_rgb . Wrgb^T) masked by [Y9 > 0]  -> activation chunks 0,1 (128 columns)
-            {
-                const uint32_t* mrow = reinterpret_cast<const uint32_t*>(tstash + kStashMaskOfs) + (8 * 128 + row) * 8;
-                const uint4 m4 = *reinterpret_cast<const uint4*>(mrow);
-                const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
-                const float* Wrgb = p.P + kernel_offset(LRGB);   // [128][3]
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float v[32];
-                    const uint32_t m = valid ? mm[g] : 0u;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = 32 * g + i;
-                        float a = dzr[0] * __ldg(Wrgb + 3 * c) + dzr[1] * __ldg(Wrgb + 3 * c + 1) + dzr[2] * __ldg(Wrgb + 3 * c + 2);
-                        v[i] = (m >> mask_bit(i)) & 1u ? a : 0.f;
-                    }
-                    uint8_t* chunk = act + (g >> 1) * kChunkBytes;
-                    const int u0 = (g & 1) * 4;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint4 o;
-                        o.x = pack2<kHalf>(v[8 * u + 0], v[8 * u + 1]);
-                        o.y = pack2<kHalf>(v[8 * u + 2], v[8 * u + 3]);
-                        o.z = pack2<kHalf>(v[8 * u + 4], v[8 * u + 5]);
-                        o.w = pack2<kHalf>(v[8 * u + 6], v[8 * u + 7]);
-                        *reinterpret_cast<uint4*>(chunk + swz(row, u0 + u)) = o;
-                    }
-                }
-            }
-            fence_proxy_async();
-            mbar_arrive(act_ready);
-            pend_dst = gst + kGradChunkZ9 * kChunkBytes; pend_bytes = 2 * kChunkBytes;
-            pend_head = true; pend_head_dst = gst + kGradChunkHead * kChunkBytes;
-
-            for (int j = 0; j < kBwdJobs; ++j) {
-                // job boundary: ship what the previous step wrote, fetch this job's ReLU bitmask
-                named_bar_sync(1 + t, kTileRows);
-                issued = false;
-                if (row == 0) {
-                    if (pend_bytes) { bulk_s2g(pend_dst, act_saddr, pend_bytes); issued = true; }
-                    if (pend_head) { bulk_s2g(pend_head_dst, head_saddr, kChunkBytes); issued = true; }
-                    if (issued) bulk_commit_group();
-                }
-                pend_bytes = 0; pend_head = false;
-                // output of job j is dZ of: j=0 -> dense_8 (no mask), j>=1 -> dense_{8-j} masked by Y_{8-j} > 0
-                uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (j >= 1) {
-                    const uint4* mrow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(tstash + kStashMaskOfs) + ((8 - j) * 128 + row) * 8);
-                    const uint4 a = mrow[0], b = mrow[1];
-                    mask[0] = a.x; mask[1] = a.y; mask[2] = a.z; mask[3] = a.w;
-                    mask[4] = b.x; mask[5] = b.y; mask[6] = b.z; mask[7] = b.w;
-                }
-                named_bar_sync(1 + t, kTileRows);
-                mbar_wait(acc_full, acc_phase);
-                acc_phase ^= 1;
-                tc_fence_after();
-                if (row == 0 && issued) bulk_wait_read_all();     // the stores had the whole MMA to drain
-                named_bar_sync(1 + t, kTileRows);
-                if (j == 0) bwd_epilogue_cols<kHalf, false, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
-                else if (j == 1) bwd_epilogue_cols<kHalf, true, true>(tmem_row, act, row, mask, s_wsig, dzs, valid);
-                else bwd_epilogue_cols<kHalf, true, false>(tmem_row, act, row, mask, s_wsig, dzs, valid);
-                tc_fence_before();
-                fence_proxy_async();
-                if (j + 1 < kBwdJobs) mbar_arrive(act_ready);     // dZ_0 (j = 8) feeds no further MMA
-                pend_dst = gst + (j == 0 ? kGradChunkZ8 : grad_chunk_Z(8 - j)) * kChunkBytes;
-                pend_bytes = 4 * kChunkBytes;
-            }
-        }
-        named_bar_sync(1 + t, kTileRows);
-        if (row == 0) {
-            if (pend_bytes) bulk_s2g(pend_dst, act_saddr, pend_bytes);
-            if (pend_head) bulk_s2g(pend_head_dst, head_saddr, kChunkBytes);
-            bulk_commit_group();
-            bulk_wait_all();
-        }
-    }
-    __syncthreads();
-    if (warp == kBMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // 2-CTA variant of the backward-data kernel (tcgen05 cta_group::2, see mlp_tc_forward_pair_kernel): M = 256
@@ -825,19 +617,13 @@ __global__ void reduce_grads_kernel(const ReduceParams rp, const float* __restri
 
 // =============================================================================================
 // host side
-static bool g_bwd_table_uploaded = false;
-
 int tc_train_create(nerfb200_ctx* ctx) {
     const BwdTable& t = bwd_table();
     for (int pz = 0; pz < 2; ++pz)
-        for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc(&ctx->packed_bwd[pz][m], (size_t)t.bytes * ctx->replicas));
-    if (!g_bwd_table_uploaded) {
-        NB_CUDA(cudaMemcpyToSymbol(c_bwd_chunks, t.c, sizeof(BwdChunk) * kBwdMaxChunks));
-        NB_CUDA(cudaMemcpyToSymbol(c_bwd_job_begin, t.job_begin, sizeof(int) * (kBwdJobs + 1)));
-        g_bwd_table_uploaded = true;
-    }
-    NB_CUDA(cudaFuncSetAttribute(bwd_data_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
-    NB_CUDA(cudaFuncSetAttribute(bwd_data_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
+        for (int m = 0; m < 2; ++m) NB_CUDA(cudaMalloc(&ctx->packed_bwd[pz][m], (size_t)t.bytes));
+    // __constant__ memory is per device: uploaded by every create, on the context's device
+    NB_CUDA(cudaMemcpyToSymbol(c_bwd_chunks, t.c, sizeof(BwdChunk) * kBwdMaxChunks));
+    NB_CUDA(cudaMemcpyToSymbol(c_bwd_job_begin, t.job_begin, sizeof(int) * (kBwdJobs + 1)));
     NB_CUDA(cudaFuncSetAttribute(bwd_data_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(bwd_data_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemTotal));
     NB_CUDA(cudaFuncSetAttribute(dw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDwSmemTotal));
@@ -855,14 +641,15 @@ int tc_train_pack(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st) 
     const int64_t units = (int64_t)t.n * (kChunkBytes / 16);
     for (int m = 0; m < 2; ++m) {
         const float* P = flat_params + (int64_t)m * kParamsPerModel;
-        pack_bwd_weights_kernel<__nv_bfloat16><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[0][m], t.n);
-        pack_bwd_weights_kernel<__half><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[1][m], t.n);
-        for (int pz = 0; pz < 2; ++pz)
-            for (int r = 1; r < ctx->replicas; ++r)
-                NB_CUDA(cudaMemcpyAsync((uint8_t*)ctx->packed_bwd[pz][m] + (size_t)r * t.bytes, ctx->packed_bwd[pz][m], t.bytes,
-                                        cudaMemcpyDeviceToDevice, st));
+        if (ctx->pack_mask & 1) {
+            pack_bwd_weights_kernel<__nv_bfloat16><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[0][m], t.n);
+            NB_LAUNCH_CHECK();
+        }
+        if (ctx->pack_mask & 2) {
+            pack_bwd_weights_kernel<__half><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[1][m], t.n);
+            NB_LAUNCH_CHECK();
+        }
     }
-    NB_LAUNCH_CHECK();
     return 0;
 }
 
@@ -911,7 +698,12 @@ static void plan_dw(const DwJob* jobs, int grid, DwParams& dp, ReduceParams& rp)
 // phase next to the fine model's backward-data phase on disjoint SMs and keep reads and writes in flight together.
 int tc_backward_data(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const float* flat_params, const float* d_rgb,
                      const float* d_sigma, void* workspace, void* stash, int max_sms, cudaStream_t st) {
-    if (!ctx->packed_valid) { set_error("mlp_backward: pack_weights has not been called"); return NERFB200_ESTATE; }
+    int rc = check_device(ctx, "mlp_backward");
+    if (rc) return rc;
+    if (!ctx->packed_valid || !(ctx->packed_mask & (half ? 2 : 1))) {
+        set_error("mlp_backward: pack_weights has not been called for this precision");
+        return NERFB200_ESTATE;
+    }
     NB_CHECK_ARG(workspace && stash, "mlp_backward: workspace and stash required");
     const int64_t R = B * S;
     if (R == 0) return 0;
@@ -923,18 +715,11 @@ int tc_backward_data(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, c
 
     BwdParams bp;
     bp.wimg = (const uint8_t*)ctx->packed_bwd[half ? 1 : 0][which];
-    bp.wimg_stride = bwd_table().bytes; bp.replicas = ctx->replicas;
     bp.P = P; bp.stash = (const uint8_t*)stash; bp.gstash = gstash; bp.d_rgb = d_rgb; bp.d_sigma = d_sigma; bp.R = R; bp.num_tiles = num_tiles;
-    const int pairs = (num_tiles + 1) / 2;
-    const int grid = pairs < sms ? pairs : sms;
-    static const bool use_pair = getenv("NERFB200_TC_PAIR") ? atoi(getenv("NERFB200_TC_PAIR")) != 0 : true;
-    if (use_pair) {
-        const int quads = (num_tiles + 3) / 4;
-        const int clusters = quads < sms / 2 ? quads : sms / 2;
-        if (half) bwd_data_pair_kernel<true><<<2 * clusters, kBThreads, kBSmemTotal, st>>>(bp);
-        else bwd_data_pair_kernel<false><<<2 * clusters, kBThreads, kBSmemTotal, st>>>(bp);
-    } else if (half) bwd_data_kernel<true><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
-    else bwd_data_kernel<false><<<grid, kBThreads, kBSmemTotal, st>>>(bp);
+    const int quads = (num_tiles + 3) / 4;
+    const int clusters = quads < sms / 2 ? quads : sms / 2;
+    if (half) bwd_data_pair_kernel<true><<<2 * clusters, kBThreads, kBSmemTotal, st>>>(bp);
+    else bwd_data_pair_kernel<false><<<2 * clusters, kBThreads, kBSmemTotal, st>>>(bp);
     NB_LAUNCH_CHECK();
     return 0;
 }
@@ -942,6 +727,8 @@ int tc_backward_data(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, c
 int tc_backward_weights(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, float* flat_grads, void* workspace,
                         void* stash, int max_sms, cudaStream_t st) {
     NB_CHECK_ARG(workspace && stash, "mlp_backward: workspace and stash required");
+    int rc = check_device(ctx, "mlp_backward_weights");
+    if (rc) return rc;
     const int64_t R = B * S;
     if (R == 0) return 0;
     const int num_tiles = (int)tiles_of(R);

@@ -107,6 +107,16 @@ template <bool kHalf> __device__ __forceinline__ uint32_t pack2(float a, float b
     }
 }
 
+// the fp32 value of the low / high 16-bit half of a pack2 word
+template <bool kHalf> __device__ __forceinline__ float unpack_lo(uint32_t w) {
+    if constexpr (kHalf) return __low2float(*reinterpret_cast<const __half2*>(&w));
+    else return __uint_as_float(w << 16);
+}
+template <bool kHalf> __device__ __forceinline__ float unpack_hi(uint32_t w) {
+    if constexpr (kHalf) return __high2float(*reinterpret_cast<const __half2*>(&w));
+    else return __uint_as_float(w & 0xffff0000u);
+}
+
 // pack2 with the ReLU folded into the conversion (cvt.rn.relu: negative results become +0): one F2FP
 // instead of F2FP + HMNMX2. The first PTX source operand lands in the upper half.
 template <bool kHalf> __device__ __forceinline__ uint32_t pack2_relu(float a, float b) {

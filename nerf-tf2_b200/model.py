@@ -11,6 +11,7 @@ gradient is one flat buffer (a single NCCL all-reduce in data-parallel training,
 and Adam is one fused launch.
 """
 import ctypes as C
+import functools
 import math
 import os
 
@@ -18,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops, ray_utils
-from ._lib import BF16, COARSE, FINE, FP16, FP32, PARAMS_PER_MODEL, PARAMS_TOTAL, check, load, ptr, stream_ptr
+from ._lib import BF16, COARSE, FINE, FP16, FP32, TF32, PARAMS_PER_MODEL, PARAMS_TOTAL, check, load, ptr, stream_ptr
 from .data import RayDataset
 
 LAYER_NAMES = [f"dense_{i}" for i in range(10)] + ["rgb", "sigma"]
@@ -52,6 +53,16 @@ def glorot_uniform_params(seed):
     return flat
 
 
+def _on_device(fn):
+    """Runs a NeRF method with the model's GPU as the current device: the C ABI launches on the current
+    device's current stream and the context is bound to the device it was created on."""
+    @functools.wraps(fn)
+    def inner(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return inner
+
+
 class PositionalEncoder:
     """PositionalEncoder (core/model.py:289-332). Standalone layer object for API parity; inside
     the fused MLP kernel the encoding is computed on chip and never written to HBM."""
@@ -69,9 +80,10 @@ class PositionalEncoder:
 class Variable:
     """A named view into the flat parameter buffer (stands in for tf.Variable)."""
 
-    def __init__(self, name, view):
+    def __init__(self, name, view, owner=None):
         self.name = name
         self._view = view
+        self._owner = owner          # the NeRF whose packed tensor-core images go stale when this changes
         self.shape = tuple(view.shape)
 
     def numpy(self):
@@ -82,6 +94,8 @@ class Variable:
 
     def assign(self, arr):
         self._view.copy_(torch.as_tensor(np.asarray(arr), dtype=torch.float32).reshape(self.shape))
+        if self._owner is not None:
+            self._owner._dirty = True
 
 
 class SubModel:
@@ -123,7 +137,8 @@ class SubModel:
         R = xyz.shape[0]
         t0 = torch.zeros((R, 1), device=xyz.device, dtype=torch.float32)
         # a row is a 1-sample ray with o = xyz, t = 0: o + 0*d == o exactly
-        rgb, sigma = self._nerf._mlp(self.which, xyz.contiguous(), dirs.contiguous(), t0, precision=precision)
+        with torch.cuda.device(self._nerf.device):
+            rgb, sigma = self._nerf._mlp(self.which, xyz.contiguous(), dirs.contiguous(), t0, precision=precision)
         return rgb, sigma.reshape(R, 1)
 
 
@@ -158,8 +173,9 @@ class _Adam:
 
     def apply_gradients(self, flat_grads):
         n = self._nerf.flat_params.numel()
-        check(load().nerfb200_adam_step(n, ptr(self._nerf.flat_params), ptr(flat_grads), ptr(self.m), ptr(self.v),
-                                        self.iterations, stream_ptr()), "adam_step")
+        with torch.cuda.device(self._nerf.device):
+            check(load().nerfb200_adam_step(n, ptr(self._nerf.flat_params), ptr(flat_grads), ptr(self.m), ptr(self.v),
+                                            self.iterations, stream_ptr()), "adam_step")
         self.iterations += 1
         self._nerf._dirty = True
 
@@ -174,15 +190,22 @@ class NeRF:
     """NeRF(Model) (core/model.py:18-287)."""
 
     def __init__(self, params, precision="bf16", train_precision=None, seed=0, device=None,
-                 rng_seed=0, render_chunk=32768):
+                 rng_seed=0, render_chunk=32768, precise_last=True):
+        """`precision`: MLP arithmetic of forward/predict -- "bf16" (default), "fp16", "tf32" (tcgen05 tensor cores,
+        fp32 accumulate) or "fp32" (CUDA-core check path). `train_precision` defaults to `precision` (bf16 for a
+        tf32 model: tf32 is a render precision). `precise_last`: the tensor-core forwards recompute sigma of every
+        ray's last sample with split operands (NERFB200_OPT_PRECISE_LAST)."""
         _lib.require_cuda()
         load()
         self.params = params
         self.white_bg = params.system.white_bg
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else precision
-        tp = precision if train_precision is None else train_precision
+        tp = train_precision if train_precision is not None else ("bf16" if self.precision == TF32 else self.precision)
         self.train_precision = _lib.PRECISIONS[tp] if isinstance(tp, str) else tp
+        self.precise_last = bool(precise_last)
         self.rng_seed = rng_seed
         self.render_chunk = render_chunk
         self.val_cache = []
@@ -192,6 +215,12 @@ class NeRF:
             h = C.c_void_p()
             check(load().nerfb200_create(C.byref(h)), "create")
             self._ctx = h
+            # operand images are packed only for the precisions this model uses (others are added on first use)
+            self._pack_mask = 0
+            for pz in (self.precision, self.train_precision):
+                self._pack_mask |= _lib.PACK_BIT.get(pz, 0)
+            check(load().nerfb200_set_option(h, _lib.OPT_PACK_MASK, self._pack_mask or 1), "set_option")
+            check(load().nerfb200_set_option(h, _lib.OPT_PRECISE_LAST, int(self.precise_last)), "set_option")
         # SMs given to the coarse model's weight-gradient phase while the fine model's backward-data phase runs on the
         # others; 0 (default) = plain sequential backward. Measured on B200: 48 SMs 5.45 ms/step
         # vs 5.43 sequential, 32 and 64 worse - both phases slow down in proportion to the SMs they lose, so the overlap
@@ -209,7 +238,7 @@ class NeRF:
                 shape = (fi, fo) if vi % 2 == 0 else (fo,)
                 o = mi * PARAMS_PER_MODEL + offs[vi]
                 n = int(np.prod(shape))
-                var = Variable(nm, self.flat_params[o:o + n].view(shape))
+                var = Variable(nm, self.flat_params[o:o + n].view(shape), owner=self)
                 var._ofs, var._n = o, n
                 self._variables.append(var)
         self.coarse_model = SubModel(self, COARSE, "coarse")
@@ -270,7 +299,12 @@ class NeRF:
             skip_optimizer = bool(getattr(load, "skip_optimizer", False)) if load is not None else False
         checkpoint.set_everything(self, load_dir, load_tag, skip_optimizer)
 
-    def _sync_packed(self):
+    def _sync_packed(self, precision=None):
+        bit = _lib.PACK_BIT.get(precision, 0)
+        if bit and not (self._pack_mask & bit):          # a precision this model has not used before
+            self._pack_mask |= bit
+            check(load().nerfb200_set_option(self._ctx, _lib.OPT_PACK_MASK, self._pack_mask), "set_option")
+            self._dirty = True
         if self._dirty:
             check(load().nerfb200_pack_weights(self._ctx, ptr(self.flat_params), stream_ptr()), "pack_weights")
             self._dirty = False
@@ -289,7 +323,7 @@ class NeRF:
         R = B * S
         rgb = torch.empty((R, 3), device=self.device, dtype=torch.float32)
         sigma = torch.empty((R,), device=self.device, dtype=torch.float32)
-        self._sync_packed()
+        self._sync_packed(precision)
         training = stash is not None
         wsb = load().nerfb200_mlp_workspace_bytes(R, precision, 0)
         ws = self._scratch("mlp_ws", wsb) if (wsb > 0 and not training) else None
@@ -309,6 +343,7 @@ class NeRF:
                                            ptr(stash, torch.uint8, allow_none=True), stream_ptr()), "mlp_backward")
 
     # ---------------------------------------------------------------------------- the ray march
+    @_on_device
     def forward(self, rays_o, rays_d, near, far, u_coarse=None, u_fine=None, ray0=0, precision=None,
                 need_weights=True, _train=None):
         """NeRF.forward (core/model.py:57-125): stratified sampling -> coarse MLP -> compositing ->
@@ -408,13 +443,17 @@ class NeRF:
                                                 ptr(tr["st_f"], u8), 0, stream_ptr()), "mlp_backward_weights")
         return loss, pp_c, pp_f
 
-    def train_step(self, data, u_coarse=None, u_fine=None, ray0=0):
+    @_on_device
+    def train_step(self, data, u_coarse=None, u_fine=None, ray0=None):
         """NeRF.train_step (core/model.py:127-180). `data` = ((rays_o, rays_d, near, far), (rgb,)) --
-        this rank's shard of the batch when data-parallel."""
+        this rank's shard of the batch when data-parallel. The in-kernel Philox streams are keyed by
+        (seed, step, ray0 + ray); `ray0` defaults to rank * B so that ranks draw independent noise."""
         if self.optimizer is None:
             self.compile()
         (ro, rd, near, far), (rgb,) = data
         ro, rd, near, far, rgb = (self._to_device(a) for a in (ro, rd, near, far, rgb))
+        if ray0 is None:
+            ray0 = self.rank * int(ro.shape[0])
         loss, _, _ = self._loss_and_grads(ro, rd, near, far, rgb, u_coarse, u_fine, ray0)
         if self.world_size > 1:
             import torch.distributed as dist
@@ -425,11 +464,12 @@ class NeRF:
         self.last_loss = loss
         return {m.name: m.result_async() for m in self.metrics}     # no device sync: see PSNRMetric.result_async
 
-    def test_step(self, data, u_coarse=None, u_fine=None):
+    @_on_device
+    def test_step(self, data, u_coarse=None, u_fine=None, ray0=0):
         """NeRF.test_step (core/model.py:182-223): forward + metric update on the fine output."""
         (ro, rd, near, far), (rgb,) = data
         ro, rd, near, far, rgb = (self._to_device(a) for a in (ro, rd, near, far, rgb))
-        _, pp_f = self.forward(ro, rd, near, far, u_coarse, u_fine, need_weights=False)
+        _, pp_f = self.forward(ro, rd, near, far, u_coarse, u_fine, ray0, need_weights=False)
         for m in self.metrics:
             m.update_state(rgb, pp_f["pred_rgb"])
         return {m.name: m.result_async() for m in self.metrics}
@@ -495,13 +535,16 @@ class NeRF:
             self.compile()
         for m in self.metrics:
             m.reset_states()
+        ray0 = 0
         for batch in x:
-            self.test_step(batch)
+            self.test_step(batch, ray0=ray0)         # every validation batch draws its own sampling noise
+            ray0 += int(batch[0][0].shape[0])
         self._metric_allreduce()
         res = {m.name: m.result() for m in self.metrics}
         return res if return_dict else (list(res.values())[0] if len(res) == 1 else list(res.values()))
 
     # ------------------------------------------------------------------------------- rendering
+    @_on_device
     def render_rays(self, rays_o, rays_d, near, far, ray0=0, need_weights=False, u_coarse=None, u_fine=None,
                     keep_coarse=True):
         """Ray-march an arbitrary number of device-resident rays in chunks of `render_chunk`. Returns
@@ -524,6 +567,7 @@ class NeRF:
         cat = lambda ds: {k: torch.cat([d[k] for d in ds], dim=0) for k in ds[0]} if ds else {}
         return cat(outs_c), cat(outs_f)
 
+    @_on_device
     def predict(self, x=None, return_weights=True, as_numpy=True, **_):
         """Model.predict over a render dataset (main/eval.py:48, main/render.py:85): returns
         (dict_CM, dict_FM) with keys acc_map [N], weights [N,S], pred_rgb [N,3], pred_depth [N],
@@ -586,7 +630,8 @@ class NeRF:
                     if v.dim() > 1 and v.shape[1] > 4:      # per-sample `weights`: too large to keep pinned copies of
                         out[k] = v
                         continue
-                    pin = pinned(("out", which, chunk_idx, k), (-(-v.shape[0] // 65536) * 65536,) + tuple(v.shape[1:]))
+                    # two staging slots: chunk i-2 has been drained before chunk i is staged (see flush)
+                    pin = pinned(("out", which, chunk_idx & 1, k), (-(-v.shape[0] // 65536) * 65536,) + tuple(v.shape[1:]))
                     pin[:v.shape[0]].copy_(v, non_blocking=True)
                     v.record_stream(cs)
                     out[k] = pin[:v.shape[0]]
@@ -677,7 +722,12 @@ def get_coarse_or_fine_model(model_name, num_units=256, params=None, **kw):
 
 def setup_model(params, **kw):
     """setup_model (core/model.py:396-432): Adam(ExponentialDecay(5e-4, 500000, 0.1)) + PSNRMetric; weights and
-    optimiser state are restored from params.model.load.* when `set_weights` is on."""
+    optimiser state are restored from params.model.load.* when `set_weights` is on. `params.system.tf_seed`
+    (main/train.py:20; may be None) seeds the sampling noise unless `rng_seed` is given."""
+    if "rng_seed" not in kw:
+        tf_seed = getattr(getattr(params, "system", None), "tf_seed", None)
+        if tf_seed is not None:
+            kw["rng_seed"] = int(tf_seed)
     nerf = NeRF(params=params, **kw)
     nerf.compile(optimizer="adam", metrics=[ops.PSNRMetric()],
                  run_eagerly=getattr(params.system, "run_eagerly", False))

@@ -1,5 +1,5 @@
 """Developer tool: time the fused forward with and without the training stash (fine-model shape of a 4096-ray step).
-With NERFB200_TC_DEBUG=3|4|5 the debug instantiation drops the stash stores / the ReLU bitmask stores / both, which
+With a mode argument 3|4|5 (nerfb200_set_option NERFB200_OPT_DEBUG) the debug instantiation drops the stash stores / the ReLU bitmask stores / both, which
 attributes the training forward's slowdown over the inference forward (results are then meaningless)."""
 import os
 import sys
@@ -8,6 +8,9 @@ sys.path.insert(0, ".")
 import nerf_tf2_b200 as nb
 from nerf_tf2_b200 import _lib
 nerf = nb.setup_model(nb.make_params(), precision="bf16")
+mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+if mode:
+    _lib.check(_lib.load().nerfb200_set_option(nerf._ctx, _lib.OPT_DEBUG, mode), "set_option")
 B, S = 4096, 192
 ro = torch.zeros((B, 3), device="cuda"); rd = torch.nn.functional.normalize(torch.randn((B, 3), device="cuda"), dim=1)
 t = torch.sort(torch.rand((B, S), device="cuda") * 0.85 + 0.425, dim=1)[0].contiguous()
@@ -20,5 +23,5 @@ def run(st, n=10):
     for _ in range(n): nerf._mlp(1, ro, rd, t, _lib.BF16, st)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-print(f"TC_DEBUG={os.environ.get('NERFB200_TC_DEBUG', '-')} rows {B*S}: inference {run(None):.3f} ms, "
+print(f"debug mode {mode} rows {B*S}: inference {run(None):.3f} ms, "
       f"training (stash {stash.numel()/1e9:.2f} GB) {run(stash):.3f} ms")
