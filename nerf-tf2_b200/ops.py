@@ -65,9 +65,21 @@ class PSNRMetric:
             self.state = torch.zeros(2, device=device, dtype=torch.float32)
 
     def update_state(self, y_true, y_pred, sample_weight=None):
+        """state += [sum((y_true - y_pred)^2), number of rays] (core/ops.py:204-220), accumulated by the same kernel
+        that accumulates it during train_step (nerfb200_mse_loss_grad with no loss / gradient outputs)."""
+        from ._lib import check, load, ptr, stream_ptr
+        y_true = y_true.to(torch.float32).contiguous()
+        y_pred = y_pred.to(torch.float32).contiguous()
+        assert y_true.shape == y_pred.shape and y_true.dim() == 2 and y_true.shape[1] == 3
         self._ensure(y_true.device)
-        self.state[0] += torch.sum(torch.square(y_true - y_pred))
-        self.state[1] += float(y_true.shape[0])
+        B = int(y_true.shape[0])
+        if not y_true.is_cuda:       # a metric object fed HOST arrays (like psnr_metric_numpy): host arithmetic
+            self.state[0] += torch.sum(torch.square(y_true - y_pred))
+            self.state[1] += float(B)
+            return
+        with torch.cuda.device(y_true.device):
+            check(load().nerfb200_mse_loss_grad(B, B, ptr(y_pred), ptr(y_true), None, None, ptr(self.state), stream_ptr()),
+                  "mse_loss_grad")
 
     @staticmethod
     def _psnr(sq, cnt):
