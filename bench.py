@@ -36,7 +36,13 @@ H = W = 800
 N_COARSE, N_FINE = 64, 128
 FLOP_PER_ROW = 1186816                      # 2 x 593 408 MAC, unpadded
 ROWS_PER_RAY = N_COARSE + (N_COARSE + N_FINE)
+# `ncu -i <report> --page raw --csv` exports of this round's `ncu --set full` captures (traffic = dram bytes per launch)
+NCU_MLP_CSV = {"bf16": "r2_ncu_full_mlp_pair_raw.csv", "fp16": "r2_ncu_full_mlp_pair_raw.csv", "tf32": "r2_ncu_full_mlp_tf32_raw.csv"}
+NCU_HBM_CSV = "r2_ncu_full_hbm_kernels_raw.csv"
 REF_SAMPLE_RAYS = 1024                      # bounded sample per step for the CPU arm
+METRIC = "rendered rays/s (64+128 samples, 800x800)"
+WORKLOAD = ("BASELINE.json configs[1]: synthetic lego-shaped 800x800 single-view render, 64+128 samples, random-init "
+            "coarse+fine 8x256 MLPs, white_bg, perturb on (in-kernel Philox)")
 
 
 def peaks():
@@ -89,42 +95,51 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_rays_per_s(sample_rays, seed=0):
-    """The reference arithmetic on the host cores: oracle forward (random uniforms fixed by seed)."""
-    import torch
-    from oracle import model as om, scene as osc
-    torch.set_num_threads(os.cpu_count())
-    v = osc.synthetic_view(H, W, view=0)
-    rng = np.random.default_rng(seed)
-    sel = rng.choice(H * W, size=sample_rays, replace=False)
-    w = om.init_weights(0)
-    uc = rng.random((sample_rays, N_COARSE), dtype=np.float32)
-    uf = rng.random((sample_rays, N_FINE), dtype=np.float32)
-    t0 = time.time()
-    om.forward(w, v["rays_o"][sel], v["rays_d"][sel], v["near"][sel], v["far"][sel], N_COARSE, N_FINE,
-               lin_inv_depth=True, perturb=True, white_bg=True, u_coarse=uc, u_fine=uf)
-    dt = time.time() - t0
-    return sample_rays / dt, torch.get_num_threads()
+class OracleArm:
+    """The reference arithmetic on the host cores: oracle forward (fixed uniforms). Scene, weights and the ray sample
+    are built ONCE; a timed call is the forward only (coarse sampling -> MLP -> integrator -> hierarchical sampling ->
+    MLP -> integrator), what the reference's predict_step spends its time in."""
+
+    def __init__(self, view_hw, sample_rays=None, seed=0):
+        import torch
+        from oracle import model as om, scene as osc
+        self.om = om
+        self.threads = os.cpu_count()
+        torch.set_num_threads(self.threads)
+        h, w = view_hw
+        v = osc.synthetic_view(h, w, view=0)
+        rng = np.random.default_rng(seed)
+        n = h * w
+        sel = np.arange(n) if sample_rays is None or sample_rays >= n else rng.choice(n, size=sample_rays, replace=False)
+        self.n = len(sel)
+        self.rays = tuple(np.ascontiguousarray(v[k][sel]) for k in ("rays_o", "rays_d", "near", "far"))
+        self.w = om.init_weights(0)
+        self.uc = rng.random((self.n, N_COARSE), dtype=np.float32)
+        self.uf = rng.random((self.n, N_FINE), dtype=np.float32)
+
+    def step(self):
+        t0 = time.time()
+        self.om.forward(self.w, *self.rays, N_COARSE, N_FINE, lin_inv_depth=True, perturb=True, white_bg=True,
+                        u_coarse=self.uc, u_fine=self.uf)
+        return time.time() - t0
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    for i in range(args.warmup):
-        oracle_rays_per_s(REF_SAMPLE_RAYS, seed=i)
-    t0 = time.time()
-    cores = 1
-    for i in range(args.steps):
-        _, cores = oracle_rays_per_s(REF_SAMPLE_RAYS, seed=100 + i)
-    dt = time.time() - t0
-    val = REF_SAMPLE_RAYS * args.steps / dt
-    sample = f"{REF_SAMPLE_RAYS} random rays of the 800x800 view per step, coarse+fine 64+128, fp32 torch-CPU/NumPy oracle"
-    line = {"impl": "reference", "metric": "rendered rays/s (64+128 samples, 800x800)", "value": val, "unit": "rays/s",
+    arm = OracleArm((H, W), REF_SAMPLE_RAYS)
+    for _ in range(args.warmup):
+        arm.step()
+    dt = sum(arm.step() for _ in range(args.steps))
+    val = arm.n * args.steps / dt
+    sample = (f"{arm.n} random rays of the 800x800 view per step (scene, weights and sample built once outside the timed "
+              f"steps), coarse+fine 64+128, fp32 torch-CPU/NumPy oracle")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: synthetic lego-shaped 800x800 view, 64+128 samples (bounded sample)"},
-            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD + " (bounded sample)"},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": arm.threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -241,11 +256,34 @@ def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_
     return results
 
 
+def ncu_traffic(csv_name, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_substr`, averaged over the launches in a
+    committed `ncu -i <rep> --page raw --csv` export under profiles/ (an `ncu --set full` capture). None if absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None, None
+    rows = list(csv.reader(open(path)))
+    if len(rows) < 3:
+        return None, None
+    hdr, units = rows[0], rows[1]
+    try:
+        kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0)
+            for r in rows[2:] if len(r) == len(hdr) and kernel_substr in r[kn]]
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals), f"profiles/{csv_name}: {len(vals)} launch(es) of {kernel_substr}, ncu --set full"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import nerf_tf2_b200 as nb
-    from nerf_tf2_b200 import ray_utils as ru, _lib
+    from nerf_tf2_b200 import ray_utils as ru, _lib, render as nbrender
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,127 +303,180 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_ranks(x):
+        return nb.dist.max_over_ranks(x, dev) if world > 1 else x
+
+    lib = _lib.load()
+
+    def timed(fn, steps, warmup):
+        """W warm-up calls, then K calls between barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.nerfb200_launch_count()
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        timed.launches = lib.nerfb200_launch_count() - n0      # this library's kernels launched inside the timed region
+        return max_ranks(e0.elapsed_time(e1)), t0, time.time()
+
     pk = peaks()
+    tensor_peak = pk["tensor"] * (0.5 if args.precision == "tf32" else 1.0)
+    tensor_burst = pk["tensor_burst"] * (0.5 if args.precision == "tf32" else 1.0)
     params = nb.make_params({"system": {"white_bg": True}}, N_coarse=N_COARSE, N_fine=N_FINE, perturb=True, lin_inv_depth=True)
     nerf = nb.setup_model(params, precision=args.precision, seed=0, rng_seed=1234, render_chunk=args.chunk)
     scene = nb.scene.SyntheticScene(H, W, num_cameras=max(8, world))
-    view = rank % len(scene)
-    ds_dev = nb.create_dataset_for_render(H, W, scene.poses[view], scene.bounds, scene.K, batch_size=4096, on_device=True)
-    ro, rd, near, far = ds_dev.inputs
-    n_rays = ro.shape[0]
+    n_rays = H * W
+    warmup = max(args.warmup, 3)
 
-    lib = _lib.load()
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
-        nerf.render_rays(ro, rd, near, far, need_weights=False)
-    barrier()
+    # ---- headline (`value`): ONE 800x800 view per step, its rays sharded over the ranks (contiguous ranges), replicated
+    # weights, no data-path collective, and the final gather of the [H*W,5] image rows to rank 0 INSIDE the timed region
+    a0, b0 = nb.dist.shard_range(n_rays, rank, world)
+    shard = nb.create_dataset_for_render(H, W, scene.poses[0], scene.bounds, scene.K, batch_size=4096, on_device=True,
+                                         ray0=a0, n_rays=b0 - a0).inputs
+    keep = {}
 
-    # ---- timed region 1: device-resident inputs, the kernel path only -> `value`
+    def step_view():
+        keep["rows"] = nbrender.render_view_sharded(nerf, H, W, scene.poses[0], scene.bounds, scene.K, rays=shard, dst=0)
+
     clocks = ClockSampler(local) if rank == 0 else None
-    barrier()
-    launches0 = lib.nerfb200_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tw0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        nerf.render_rays(ro, rd, near, far, need_weights=False)
-    e1.record()
-    barrier()
-    tw1 = time.time()
-    launches = lib.nerfb200_launch_count() - launches0
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        ms = nb.dist.max_over_ranks(ms, dev)
+    ms, tw0, tw1 = timed(step_view, args.steps, warmup)
+    launches_timed = timed.launches
     clk = clocks.stop(tw0, tw1) if clocks else None
-    value = world * n_rays * args.steps / (ms / 1e3)
+    value = n_rays * args.steps / (ms / 1e3)
+    gather_bytes = n_rays * 5 * 4 if world > 1 else 0
 
-    # ---- timed region 1b: the same K steps again with CUDA-event brackets around every C-ABI launch
-    # (on the launching stream) -> per-kernel durations for the roofline objects
+    # ---- the same K steps again with CUDA-event brackets around every C-ABI launch (on the launching stream)
+    # -> per-kernel durations for the roofline objects (this rank's shard)
     kt = KernelTimer(torch)
     orig = (nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse)
     nerf._mlp = kt.wrap("mlp", nerf._mlp)
     ru.post_process_model_output = kt.wrap("composite", ru.post_process_model_output)
     ru.sample_fine = kt.wrap("sample_fine", ru.sample_fine)
     ru.sample_coarse = kt.wrap("sample_coarse", ru.sample_coarse)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        nerf.render_rays(ro, rd, near, far, need_weights=False)
-    f1.record()
-    barrier()
-    ms_b = f0.elapsed_time(f1)
+    ms_b, _, _ = timed(step_view, args.steps, 0)
     nerf._mlp, ru.post_process_model_output, ru.sample_fine, ru.sample_coarse = orig
+    my_rays = b0 - a0
 
     tot = kt.totals()
     mlp_ms, mlp_n = tot["mlp"]
-    mlp_flop = args.steps * n_rays * ROWS_PER_RAY * FLOP_PER_ROW
+    mlp_flop = args.steps * my_rays * ROWS_PER_RAY * FLOP_PER_ROW
     mlp_tflops = mlp_flop / (mlp_ms / 1e3) / 1e12
     comp_ms, comp_n = tot["composite"]
     # coarse: 24*S+20 B/ray with the [B,S] weights store; fine in render mode skips it: 20*S+20
-    comp_bytes = args.steps * n_rays * ((24 * N_COARSE + 20) + (20 * (N_COARSE + N_FINE) + 20))
+    comp_bytes = args.steps * my_rays * ((24 * N_COARSE + 20) + (20 * (N_COARSE + N_FINE) + 20))
     sf_ms, sf_n = tot["sample_fine"]
     # weights 4Nc + bin edges 4(Nc+1) + t_coarse 4Nc read, t_sorted 4(Nc+Nf) written; u generated in-kernel
-    sf_bytes = args.steps * n_rays * (4 * N_COARSE * 2 + 4 * (N_COARSE + 1) + 4 * (N_COARSE + N_FINE))
+    sf_bytes = args.steps * my_rays * (4 * N_COARSE * 2 + 4 * (N_COARSE + 1) + 4 * (N_COARSE + N_FINE))
     sc_ms, sc_n = tot["sample_coarse"]
     # near/far read, t [B,Nc] and bin edges [B,Nc+1] written; u generated in-kernel
-    sc_bytes = args.steps * n_rays * (8 + 4 * N_COARSE + 4 * (N_COARSE + 1))
-    traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic, traffic_note = tj.get("mlp_dram_bytes_per_launch"), tj.get("note")
-    roofline = {"bound": "tensor", "kernel": "mlp_tc_forward_pair_kernel (fused encoding + 8x256 MLP on tcgen05 cta_group::2; coarse and fine launches)",
-                "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
-                "peak_kind": f"bf16 sustained, {pk['source']}", "frac_of_burst": mlp_tflops / pk["tensor_burst"],
-                "traffic": traffic, "launches": mlp_n, "avg_launch_ms": mlp_ms / mlp_n,
-                "share_of_step": mlp_ms / ms_b, "traffic_note": traffic_note}
+    sc_bytes = args.steps * my_rays * (8 + 4 * N_COARSE + 4 * (N_COARSE + 1))
+    mlp_kernel = "mlp_tf32_forward_kernel" if args.precision == "tf32" else "mlp_tc_forward_pair_kernel"
+    traffic, traffic_src = ncu_traffic(NCU_MLP_CSV.get(args.precision, ""), mlp_kernel)
+    roofline = {"bound": "tensor",
+                "kernel": f"{mlp_kernel} (fused encoding + 8x256 MLP on tcgen05 cta_group::2; coarse, fine and split last-sample launches)",
+                "achieved": mlp_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": mlp_tflops / tensor_peak,
+                "peak_kind": (f"bf16 sustained, {pk['source']}" if args.precision != "tf32"
+                              else f"half of bf16 sustained ({pk['source']}): kind::tf32 runs at half the 16-bit rate"),
+                "frac_of_burst": mlp_tflops / tensor_burst,
+                "traffic": traffic, "traffic_source": traffic_src, "traffic_scope": "one fine launch of 65536 rays x 192 samples",
+                "launches": mlp_n, "avg_launch_ms": mlp_ms / mlp_n, "share_of_step": mlp_ms / ms_b}
     in_step = {"composite": comp_bytes / (comp_ms / 1e3) / 1e9, "sample_fine": sf_bytes / (sf_ms / 1e3) / 1e9,
                "sample_coarse": sc_bytes / (sc_ms / 1e3) / 1e9}
-    alone = {r["key"]: r for r in hbm_kernels_alone(rays=args.chunk)}
-    # the integrator as the render uses it: one coarse launch (weights out) + one fine launch (no weights) per chunk
-    ca, cf = alone["composite_coarse"], alone["composite_fine"]
-    comp_alone = (ca["bytes_per_ray"] + cf["bytes_per_ray"]) * ca["rays"] / ((ca["us"] + cf["us"]) * 1e-6) / 1e9
-    how = ("achieved: back-to-back launches of the kernel alone at the render chunk size, CUDA events around the batch, inputs "
-           "rotated through sets > 2x L2; in_step_GBps: CUDA-event brackets around each single launch inside the render step "
-           "(includes the launch gaps, which are comparable to a 15-50 us kernel)")
-    tk = (tj.get("hbm_kernels_dram_bytes_per_launch") if os.path.exists(tpath) else None) or {}
-    roofline_hbm = [
-        {"kernel": "composite_fwd_kernel<4,full,2 rays/warp> + <6,full> (coarse with weights, fine without)", "bound": "hbm",
-         "achieved": comp_alone, "peak": pk["hbm"], "unit": "GB/s", "frac": comp_alone / pk["hbm"],
-         "traffic": [tk.get("composite_coarse"), tk.get("composite_fine")] if tk else None,
-         "us_per_launch": [ca["us"], cf["us"]], "frac_coarse": ca["GBps"] / pk["hbm"], "frac_fine": cf["GBps"] / pk["hbm"],
-         "in_step_GBps": in_step["composite"], "launches": comp_n, "share_of_step": comp_ms / ms_b, "timing": how},
-        {"kernel": alone["sample_fine"]["kernel"], "bound": "hbm", "achieved": alone["sample_fine"]["GBps"], "peak": pk["hbm"],
-         "unit": "GB/s", "frac": alone["sample_fine"]["GBps"] / pk["hbm"], "traffic": tk.get("sample_fine"),
-         "traffic_note": tk.get("note"),
-         "us_per_launch": alone["sample_fine"]["us"], "in_step_GBps": in_step["sample_fine"], "launches": sf_n,
-         "share_of_step": sf_ms / ms_b,
-         "note": "instruction-issue bound (about 600 warp instructions per ray), not HBM bound: DESIGN.md section 4.4"},
-        {"kernel": alone["sample_coarse"]["kernel"], "bound": "hbm", "achieved": alone["sample_coarse"]["GBps"], "peak": pk["hbm"],
-         "unit": "GB/s", "frac": alone["sample_coarse"]["GBps"] / pk["hbm"], "traffic": None,
-         "us_per_launch": alone["sample_coarse"]["us"], "in_step_GBps": in_step["sample_coarse"], "launches": sc_n,
-         "share_of_step": sc_ms / ms_b},
-    ]
+    roofline_hbm = None
+    if rank == 0 and not args.no_hbm:
+        alone = {r["key"]: r for r in hbm_kernels_alone(rays=args.chunk)}
+        # the integrator as the render uses it: one coarse launch (weights out) + one fine launch (no weights) per chunk
+        ca, cf = alone["composite_coarse"], alone["composite_fine"]
+        comp_alone = (ca["bytes_per_ray"] + cf["bytes_per_ray"]) * ca["rays"] / ((ca["us"] + cf["us"]) * 1e-6) / 1e9
+        how = ("achieved: back-to-back launches of the kernel alone at the render chunk size, CUDA events around the batch, inputs "
+               "rotated through sets > 2x L2; in_step_GBps: CUDA-event brackets around each single launch inside the render step "
+               "(includes the launch gaps, which are comparable to a 15-50 us kernel)")
+        tr_cc, src_h = ncu_traffic(NCU_HBM_CSV, "composite_fwd_kernel<4")
+        tr_cf, _ = ncu_traffic(NCU_HBM_CSV, "composite_fwd_kernel<6")
+        tr_sf, _ = ncu_traffic(NCU_HBM_CSV, "sample_fine_fast_kernel")
+        roofline_hbm = [
+            {"kernel": "composite_fwd_kernel<4,full,2 rays/warp> + <6,full> (coarse with weights, fine without)", "bound": "hbm",
+             "achieved": comp_alone, "peak": pk["hbm"], "unit": "GB/s", "frac": comp_alone / pk["hbm"],
+             "traffic": [tr_cc, tr_cf], "traffic_source": src_h,
+             "us_per_launch": [ca["us"], cf["us"]], "frac_coarse": ca["GBps"] / pk["hbm"], "frac_fine": cf["GBps"] / pk["hbm"],
+             "in_step_GBps": in_step["composite"], "launches": comp_n, "share_of_step": comp_ms / ms_b, "timing": how},
+            {"kernel": alone["sample_fine"]["kernel"], "bound": "hbm", "achieved": alone["sample_fine"]["GBps"], "peak": pk["hbm"],
+             "unit": "GB/s", "frac": alone["sample_fine"]["GBps"] / pk["hbm"], "traffic": tr_sf, "traffic_source": src_h,
+             "us_per_launch": alone["sample_fine"]["us"], "in_step_GBps": in_step["sample_fine"], "launches": sf_n,
+             "share_of_step": sf_ms / ms_b},
+            {"kernel": alone["sample_coarse"]["kernel"], "bound": "hbm", "achieved": alone["sample_coarse"]["GBps"], "peak": pk["hbm"],
+             "unit": "GB/s", "frac": alone["sample_coarse"]["GBps"] / pk["hbm"], "traffic": None,
+             "us_per_launch": alone["sample_coarse"]["us"], "in_step_GBps": in_step["sample_coarse"], "launches": sc_n,
+             "share_of_step": sc_ms / ms_b},
+        ]
+    barrier()
 
-    # ---- timed region 2: end to end through NeRF.predict() with HOST rays (pinned), H2D + D2H included
-    e2e_val = None
+    # ---- weak scaling (secondary, N > 1): one WHOLE view per rank, no collective (round 1's headline)
+    weak = None
+    if world > 1:
+        ds_dev = nb.create_dataset_for_render(H, W, scene.poses[rank % len(scene)], scene.bounds, scene.K, batch_size=4096, on_device=True)
+        ro, rd, near, far = ds_dev.inputs
+        ms_w, _, _ = timed(lambda: nerf.render_rays(ro, rd, near, far, need_weights=False), args.steps, 1)
+        weak = {"value": world * n_rays * args.steps / (ms_w / 1e3), "unit": "rays/s", "ms_per_step": ms_w / args.steps,
+                "what": "one whole 800x800 view per rank, no collective in the timed region"}
+        del ds_dev, ro, rd, near, far
+
+    # ---- end to end: HOST rays (pinned staging inside the call), H2D + D2H inside the timed region.
+    # N = 1: the reference-facing call NeRF.predict(dataset). N > 1: every rank predicts its ray shard from host rays,
+    # the device results are gathered to rank 0 (same collective as above) and copied to the host there.
+    e2e = {"value": None, "unit": "rays/s", "h2d_bytes_per_step": n_rays * 32, "d2h_bytes_per_step": None}
     if not args.no_e2e:
-        host = tuple(a.cpu().numpy() for a in (ro, rd, near, far))
+        host = tuple(a.cpu().numpy() for a in shard)
         ds_host = nb.RayDataset.from_tensor_slices((host,)).batch(4096, drop_remainder=False)
+        if world == 1:
+            fn = lambda: nerf.predict(ds_host, return_weights=False)
+            e2e["api"] = "NeRF.predict(RayDataset of host NumPy rays, return_weights=False) -> (dict_CM, dict_FM) of NumPy arrays"
+            e2e["d2h_bytes_per_step"] = n_rays * 5 * 4 * 2
+        else:
+            fn = lambda: nbrender.predict_view_sharded(nerf, ds_host, n_rays, dst=0)
+            e2e["api"] = ("render.predict_view_sharded(host ray shard per rank) -> NeRF.predict on the shard, gather of the "
+                          "[H*W,5] rows to rank 0, D2H there")
+            e2e["d2h_bytes_per_step"] = n_rays * 5 * 4
         for _ in range(2):
-            nerf.predict(ds_host, return_weights=False)
+            fn()
         barrier()
         t0 = time.time()
         for _ in range(args.steps):
-            nerf.predict(ds_host, return_weights=False)
+            fn()
         torch.cuda.synchronize()
-        dt = time.time() - t0
-        if world > 1:
-            dt = nb.dist.max_over_ranks(dt, dev)
-        e2e_val = world * n_rays * args.steps / dt
-    h2d = n_rays * (3 + 3 + 1 + 1) * 4
-    d2h = n_rays * (3 + 1 + 1) * 4 * 2
+        dt = max_ranks(time.time() - t0)
+        e2e["value"] = n_rays * args.steps / dt
+        # the Keras-default return (per-sample `weights` [N,S] in both dicts: 0.66 GB per view), N = 1 only
+        if world == 1 and not args.no_extra:
+            nerf.predict(ds_host, return_weights=True)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for _ in range(2):
+                nerf.predict(ds_host, return_weights=True)
+            torch.cuda.synchronize()
+            dtw = (time.time() - t0) / 2
+            e2e["keras_default_return_weights"] = {"value": n_rays / dtw, "unit": "rays/s", "ms_per_view": dtw * 1e3,
+                                                   "d2h_bytes_per_step": n_rays * (5 * 2 + N_COARSE + N_COARSE + N_FINE) * 4}
+        del ds_host, host
+    barrier()
+
+    # ---- named sub-workloads: BASELINE.json configs[3] and configs[4]
+    workloads = {}
+    if not args.no_extra:
+        try:
+            workloads["cfg4_eval_200_views"] = bench_cfg4(nb, nbrender, nerf, torch, dist, world, rank, barrier, max_ranks, args)
+        except Exception as ex:  # report, do not hide
+            workloads["cfg4_eval_200_views"] = {"error": str(ex)[:300]}
+        try:
+            workloads["cfg5_1080p_128_256"] = bench_cfg5(nb, nbrender, torch, world, rank, timed, args)
+        except Exception as ex:
+            workloads["cfg5_1080p_128_256"] = {"error": str(ex)[:300]}
+    barrier()
 
     # ---- secondary metric: 4096-ray training step (coarse+fine fwd/bwd + Adam [+ all-reduce])
     train = None
@@ -393,30 +484,79 @@ def run_b200(args):
         try:
             train = bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args)
         except Exception as ex:  # report, do not hide
-            train = {"error": str(ex)[:200]}
+            train = {"error": str(ex)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rps, cores = oracle_rays_per_s(2048)
-        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": "2048 random rays of the same 800x800 view, coarse+fine 64+128, fp32 torch-CPU/NumPy oracle (TensorFlow not installable)"}
+        arm = OracleArm((100, 100))          # BASELINE.json configs[0]: the reference's own CPU-runnable case, in full
+        dt = arm.step()
+        cpu = {"value": arm.n / dt, "unit": "rays/s", "cores": arm.threads, "kind": "port", "seconds": dt,
+               "sample": "BASELINE.json configs[0] in full: one 100x100 view (10 000 rays), coarse+fine 64+128, forward only, "
+                         "fp32 torch-CPU/NumPy oracle (TensorFlow not installable)"}
 
     if rank == 0:
-        line = {"metric": "rendered rays/s (64+128 samples, 800x800)", "value": value, "unit": "rays/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": "BASELINE.json configs[1]: synthetic lego-shaped 800x800 single-view render, 64+128 samples, "
-                                       "random-init coarse+fine 8x256 MLPs, white_bg, perturb on (in-kernel Philox)",
-                           "rays_per_step_per_gpu": n_rays, "render_chunk_rays": args.chunk,
+        line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": WORKLOAD, "rays_per_step": n_rays, "rays_per_step_per_gpu": my_rays,
+                           "render_chunk_rays": args.chunk,
                            "l2": "inputs larger than L2 (per-chunk rgb/sigma/t buffers > 126 MB); no explicit flush",
-                           "parallelism": f"ray-sharded x{world} (one view per rank, no collective)"},
-                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
-                "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "NeRF.predict(RayDataset of host NumPy rays, return_weights=False)"},
-                "gpu_launches": int(launches), "clocks": clk, "train": train}
+                           "parallelism": (f"ONE view per step, rays sharded x{world} in contiguous ranges, replicated weights; "
+                                           f"final all-gather of the [H*W,5] image rows ({gather_bytes} B) inside the timed region"
+                                           if world > 1 else "single GPU, no collective"),
+                           "split_last_sample_launch": True},
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches_timed), "clocks": clk, "weak": weak, "workloads": workloads, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_cfg4(nb, nbrender, nerf, torch, dist, world, rank, barrier, max_ranks, args):
+    """BASELINE.json configs[3]: evaluate.py-shaped test-set render -- 200 views of 800x800 (main/eval.py:42-67 with the
+    depth maps of main/render.py:96-117): per view ray generation, ray march, uint8 image, PSNR against the ground-truth
+    image, depth map types 1 and 2; views dealt round-robin to the ranks, ONE all-reduce of the per-view squared errors
+    at the end. Ground truth: one synthetic uint8 image reused for every view (the PSNR value is not the point here)."""
+    n_views = args.cfg4_views
+    poses = nb.scene.SyntheticScene(H, W, num_cameras=n_views)
+    gt = np.random.default_rng(0).integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    gts = [gt] * n_views
+    run = lambda p, g: nbrender.evaluate_views(nerf, H, W, p, poses.bounds, poses.K, g, scale_factor=poses.adj_scale_factor,
+                                               depth_maps=True)
+    run(poses.poses[:world], gts[:world])       # warm-up: one view per rank
+    barrier()
+    t0 = time.time()
+    res = run(poses.poses, gts)
+    torch.cuda.synchronize()
+    dt = max_ranks(time.time() - t0)
+    rays = n_views * H * W
+    return {"what": f"{n_views} views of 800x800, 64+128 samples: rays -> march -> uint8 + PSNR + depth type_1/type_2, "
+                    f"view-sharded x{world}, final PSNR all-reduce",
+            "seconds": dt, "views_per_s": n_views / dt, "value": rays / dt, "unit": "rays/s",
+            "mlp_tflops": rays * ROWS_PER_RAY * FLOP_PER_ROW / dt / 1e12, "mean_psnr": res["mean_psnr"]}
+
+
+def bench_cfg5(nb, nbrender, torch, world, rank, timed, args):
+    """BASELINE.json configs[4]: 1920x1080 render with 128+256 samples, rays sharded over the ranks, final image gather."""
+    h5, w5, nc5, nf5 = 1080, 1920, 128, 256
+    p5 = nb.make_params({"system": {"white_bg": True}}, N_coarse=nc5, N_fine=nf5, perturb=True, lin_inv_depth=True)
+    n5 = nb.setup_model(p5, precision=args.precision, seed=0, rng_seed=99, render_chunk=args.chunk)
+    sc5 = nb.scene.SyntheticScene(h5, w5, num_cameras=8)
+    a, b = nb.dist.shard_range(h5 * w5, rank, world)
+    sh = nb.create_dataset_for_render(h5, w5, sc5.poses[0], sc5.bounds, sc5.K, batch_size=4096, on_device=True,
+                                      ray0=a, n_rays=b - a).inputs
+    keep = {}
+
+    def step():
+        keep["rows"] = nbrender.render_view_sharded(n5, h5, w5, sc5.poses[0], sc5.bounds, sc5.K, rays=sh, dst=0)
+
+    steps = 3
+    ms, _, _ = timed(step, steps, 1)
+    rays = h5 * w5
+    rows = nc5 + nc5 + nf5
+    return {"what": f"1920x1080 view, 128+256 samples, rays sharded x{world}, final gather of the [H*W,5] rows inside the timed region",
+            "ms_per_view": ms / steps, "value": rays * steps / (ms / 1e3), "unit": "rays/s",
+            "mlp_tflops": rays * rows * FLOP_PER_ROW * steps / (ms / 1e3) / 1e12}
 
 
 def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
@@ -429,12 +569,13 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
     near = torch.full((Bl, 1), scene.near, device=dev); far = torch.full((Bl, 1), scene.far, device=dev)
     rgb = torch.rand((Bl, 3), device=dev)
     p = nb.make_params({"system": {"white_bg": True}})
-    tn = nb.setup_model(p, precision=args.precision, train_precision=args.train_precision, seed=0)
+    tp = args.train_precision
+    tn = nb.setup_model(p, precision=tp if tp != "fp32" else "bf16", train_precision=tp, seed=0)
     if world > 1:
         tn.set_distributed()
     batch = ((ro, rd, near, far), (rgb,))
-    steps = max(2, min(args.steps, 10))
-    for _ in range(3):
+    steps = 50
+    for _ in range(5):
         tn.train_step(batch)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -448,9 +589,11 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
         ms = nb.dist.max_over_ranks(ms, dev)
     sps = steps / (ms / 1e3)
     flop = 3489024 * B * ROWS_PER_RAY
+    pk = peaks()
     return {"metric": "train steps/s (4096-ray batch, coarse+fine fwd/bwd + Adam, data-parallel all-reduce)",
-            "value": sps, "unit": "steps/s", "ms_per_step": ms / steps, "precision": args.train_precision,
-            "global_batch": B, "achieved_tflops": flop * sps / 1e12}
+            "value": sps, "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "precision": tp,
+            "global_batch": B, "rays_per_gpu": Bl, "achieved_tflops": flop * sps / 1e12,
+            "frac_of_sustained_peak": flop * sps / 1e12 / (pk["tensor"] * world)}
 
 
 def main():
@@ -459,12 +602,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32"],
+                    help="MLP operand width of the render (tf32 = the reference's own width on Ampere-and-later GPUs)")
     ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--chunk", type=int, default=65536, help="rays per internal render chunk")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the stand-alone timings of the HBM-bound kernels")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg4 / cfg5 sub-workloads and the return_weights=True leg")
+    ap.add_argument("--cfg4-views", type=int, default=200)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

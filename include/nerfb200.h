@@ -110,7 +110,8 @@ NERFB200_API int nerfb200_destroy(nerfb200_ctx* ctx);
  * Must be called after every optimiser step before the next forward. */
 NERFB200_API int nerfb200_pack_weights(nerfb200_ctx* ctx, const float* flat_params, void* stream);
 /* Context options.
- *   NERFB200_OPT_PRECISE_LAST (default 1): tensor-core forwards recompute sigma of the LAST sample of every
+ *   NERFB200_OPT_PRECISE_LAST (default 1; 0 off; 2 = training forwards, i.e. stash != NULL, too): tensor-core forwards
+ *     recompute sigma of the LAST sample of every
  *     ray (row ray*S + S-1, S >= 2) with error-compensated split operands, because the reference's
  *     delta_last = 1e10 (utils/ray_utils.py:459-468) turns a rounding-induced sign flip of that one ReLU
  *     output into a jump of alpha_last from 0 to 1.

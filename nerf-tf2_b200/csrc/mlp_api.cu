@@ -30,7 +30,10 @@ int nerfb200_pack_weights(nerfb200_ctx* ctx, const float* flat_params, void* str
 int nerfb200_set_option(nerfb200_ctx* ctx, int option, int value) {
     NB_CHECK_ARG(ctx != nullptr, "set_option: NULL context");
     switch (option) {
-        case NERFB200_OPT_PRECISE_LAST: ctx->precise_last = value != 0; return 0;
+        case NERFB200_OPT_PRECISE_LAST:
+            NB_CHECK_ARG(value >= 0 && value <= 2, "set_option(PRECISE_LAST): 0 off, 1 render forwards, 2 training forwards too");
+            ctx->precise_last = value;
+            return 0;
         case NERFB200_OPT_PACK_MASK:
             NB_CHECK_ARG(value >= 1 && value <= 7, "set_option(PACK_MASK): value must be a non-empty subset of bits 0..2");
             ctx->pack_mask = value;

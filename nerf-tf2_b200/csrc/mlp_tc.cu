@@ -1000,6 +1000,9 @@ int tc_forward(nerfb200_ctx* ctx, int which, int half, int64_t B, int S, const f
                     h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
         return 0;
     }
+    // training forwards (stash != NULL) take the split launch only when the option is 2: it costs two small launches
+    // per step, which matter in a data-parallel step of 512 rays per GPU, and the loss does not need it
+    if (stash && ctx->precise_last < 2) return 0;
     return tc_precise_last(ctx, which, half, B, S, ro, rd, t, sigma, stash, st);
 }
 

@@ -28,18 +28,30 @@ def shard_views(num_views, rank, world):
 
 
 def gather_rows(local, n_total, group=None, dst=None):
-    """All-gather (or gather to `dst`) row shards produced with shard_range into [n_total, ...]."""
+    """The final image gather of a ray-sharded render: row shards produced with shard_range ->
+    [n_total, ...] on every rank (or on `dst` only; other ranks get None). ONE collective: an all-gather into a single
+    [world, rows_max, ...] buffer (NCCL: one kernel over NVLink; shards are padded to the largest one, which differs
+    from the others by at most one row)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     pad = max(b - a for a, b in sizes)
-    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    buf[:local.shape[0]] = local
-    outs = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(outs, buf, group=group)
+    local = local.contiguous()
+    if local.shape[0] == pad:
+        buf = local
+    else:
+        buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        buf[:local.shape[0]] = local
+    out = torch.empty((world, pad) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    try:
+        dist.all_gather_into_tensor(out, buf, group=group)
+    except (RuntimeError, NotImplementedError):       # a backend without the single-buffer form
+        dist.all_gather(list(out.unbind(0)), buf, group=group)
     if dst is not None and rank != dst:
         return None
-    return torch.cat([o[:b - a] for o, (a, b) in zip(outs, sizes)], dim=0)
+    if n_total == world * pad:
+        return out.reshape((n_total,) + tuple(local.shape[1:]))
+    return torch.cat([out[r, :b - a] for r, (a, b) in enumerate(sizes)], dim=0)
 
 
 def allreduce_flat(flat, group=None):

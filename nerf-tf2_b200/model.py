@@ -211,7 +211,10 @@ class NeRF:
         self.val_cache = []
         with torch.cuda.device(self.device):
             self.flat_params = torch.from_numpy(glorot_uniform_params(seed)).to(self.device)
-            self.flat_grads = torch.zeros_like(self.flat_params)
+            # ONE flat buffer carries everything a data-parallel step exchanges: the gradient (coarse model, fine
+            # model) and, behind it, [loss, 0, 0, 0] -- one all-reduce per step
+            self._grad_buf = torch.zeros(PARAMS_TOTAL + 4, device=self.device, dtype=torch.float32)
+            self.flat_grads = self._grad_buf[:PARAMS_TOTAL]
             h = C.c_void_p()
             check(load().nerfb200_create(C.byref(h)), "create")
             self._ctx = h
@@ -249,6 +252,7 @@ class NeRF:
         self.metrics = []
         self.process_group = None
         self.world_size, self.rank = 1, 0
+        self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
         self._step_counter = 0
         self.last_loss = None
 
@@ -386,7 +390,7 @@ class NeRF:
 
     # -------------------------------------------------------------------------------- training
     def _loss_and_grads(self, rays_o, rays_d, near, far, rgb, u_coarse=None, u_fine=None, ray0=0,
-                        global_batch=None):
+                        global_batch=None, coarse_done=None):
         """Forward + backward of train_step (core/model.py:148-170) into self.flat_grads (local sum).
         Returns the device tensor [loss] (this rank's share of the global mean losses)."""
         prec = self.train_precision
@@ -394,7 +398,8 @@ class NeRF:
         Bg = B * self.world_size if global_batch is None else global_batch
         tr = {}
         pp_c, pp_f = self.forward(rays_o, rays_d, near, far, u_coarse, u_fine, ray0, precision=prec, _train=tr)
-        loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self._grad_buf.zero_()                       # the kernels accumulate into the gradient and the loss
+        loss = self._grad_buf[PARAMS_TOTAL:PARAMS_TOTAL + 1]
         d_c = torch.empty((B, 3), device=self.device, dtype=torch.float32)
         d_f = torch.empty((B, 3), device=self.device, dtype=torch.float32)
         metric = self.metrics[0] if self.metrics else None
@@ -406,11 +411,12 @@ class NeRF:
         check(lib.nerfb200_mse_loss_grad(B, Bg, ptr(pp_f["pred_rgb"]), ptr(rgb), ptr(d_f), ptr(loss),
                                          ptr(metric.state) if metric is not None else C.c_void_p(0),
                                          stream_ptr()), "mse_loss_grad")
-        self.flat_grads.zero_()
         ds_c, dr_c = ray_utils.composite_backward(tr["rgb_c"], tr["sig_c"], tr["t_c"], self.white_bg, d_c)
         n_dw = self._dw_overlap_sms if prec != FP32 else 0
         if n_dw <= 0:
             self._mlp_backward(COARSE, rays_o, rays_d, tr["t_c"], dr_c, ds_c, prec, tr["st_c"])
+            if coarse_done is not None:
+                coarse_done()                        # data-parallel: the coarse half of the gradient is final
             ds_f, dr_f = ray_utils.composite_backward(tr["rgb_f"], tr["sig_f"], tr["t_f"], self.white_bg, d_f)
             self._mlp_backward(FINE, rays_o, rays_d, tr["t_f"], dr_f, ds_f, prec, tr["st_f"])
             return loss, pp_c, pp_f
@@ -454,11 +460,24 @@ class NeRF:
         ro, rd, near, far, rgb = (self._to_device(a) for a in (ro, rd, near, far, rgb))
         if ray0 is None:
             ray0 = self.rank * int(ro.shape[0])
-        loss, _, _ = self._loss_and_grads(ro, rd, near, far, rgb, u_coarse, u_fine, ray0)
+        pending = []
+        coarse_done = None
+        if self.world_size > 1 and self.overlap_allreduce:
+            import torch.distributed as dist
+
+            def coarse_done():
+                # the coarse model's gradient is final before the fine model's backward starts: its all-reduce runs on
+                # NCCL's stream next to the fine backward (it takes SMs as the persistent kernels' CTAs retire)
+                pending.append(dist.all_reduce(self._grad_buf[:PARAMS_PER_MODEL], group=self.process_group, async_op=True))
+        loss, _, _ = self._loss_and_grads(ro, rd, near, far, rgb, u_coarse, u_fine, ray0, coarse_done=coarse_done)
         if self.world_size > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.flat_grads, group=self.process_group)     # one flat 4.77 MB buffer
-            dist.all_reduce(loss, group=self.process_group)
+            if pending:       # fine half + [loss] tail; then both must have landed before Adam reads them
+                pending.append(dist.all_reduce(self._grad_buf[PARAMS_PER_MODEL:], group=self.process_group, async_op=True))
+                for h in pending:
+                    h.wait()
+            else:
+                dist.all_reduce(self._grad_buf, group=self.process_group)     # ONE collective: gradient + loss
         self.optimizer.apply_gradients(self.flat_grads)
         self._step_counter += 1
         self.last_loss = loss
@@ -627,10 +646,8 @@ class NeRF:
             with torch.cuda.stream(cs):
                 cs.wait_event(done)
                 for k, v in d.items():
-                    if v.dim() > 1 and v.shape[1] > 4:      # per-sample `weights`: too large to keep pinned copies of
-                        out[k] = v
-                        continue
-                    # two staging slots: chunk i-2 has been drained before chunk i is staged (see flush)
+                    # two staging slots (the per-sample `weights` [N,S] of the Keras-default return included: 50 MB per
+                    # 65536-ray fine chunk, streamed like everything else instead of one blocking 0.66 GB copy per view): chunk i-2 has been drained before chunk i is staged (see flush)
                     pin = pinned(("out", which, chunk_idx & 1, k), (-(-v.shape[0] // 65536) * 65536,) + tuple(v.shape[1:]))
                     pin[:v.shape[0]].copy_(v, non_blocking=True)
                     v.record_stream(cs)

@@ -21,7 +21,7 @@ from ._lib import check, load, ptr, stream_ptr
 
 
 def render_view(nerf, H, W, c2w, bounds, intrinsic, gt_u8=None, scale_factor=None, depth_maps=True,
-                ray0=0, n_rays=None, c2w_W2=None):
+                ray0=0, n_rays=None, c2w_W2=None, lazy_psnr=False):
     """Renders one view (or the ray range [ray0, ray0+n_rays) of it). `c2w`/`bounds` are the W3 (scene-scaled) pose
     and bounds the rays are marched with. Returns a dict of DEVICE tensors: img_u8 [n,3], acc_map [n],
     depth_type_1 [n], depth_type_2 [n] (full views only) and `psnr` (float, eval.py definition) when `gt_u8`
@@ -47,9 +47,9 @@ def render_view(nerf, H, W, c2w, bounds, intrinsic, gt_u8=None, scale_factor=Non
           "postprocess_rgb")
     out["img_u8"] = img
     if sq is not None:
-        out["sq_err"] = sq
-        mse = float(sq.item()) / (n * 3)
-        out["psnr"] = float("inf") if mse == 0 else -10.0 * math.log10(mse)
+        out["sq_err"] = sq           # fp64 sum of squared errors of the clipped 8-bit image (device)
+        if not lazy_psnr:            # lazy: the caller turns sq_err into a PSNR later, without a sync per view
+            out["psnr"] = psnr_from_sq_err(float(sq.item()), n)
     if depth_maps and scale_factor is not None:
         out["depth_type_1"] = fine["pred_depth"] * (1 / scale_factor)
         if ray0 == 0 and n == H * W:
@@ -62,7 +62,59 @@ def render_view(nerf, H, W, c2w, bounds, intrinsic, gt_u8=None, scale_factor=Non
     return out
 
 
-def evaluate_views(nerf, H, W, poses, bounds, intrinsic, gts_u8, scale_factor=None, process_group=None):
+def psnr_from_sq_err(sq_err, n_rays):
+    """main/eval.py:57-61 + core/ops.py:249-257: -10 log10(mean over n_rays*3 of the squared error)."""
+    mse = sq_err / (n_rays * 3)
+    return float("inf") if mse == 0 else -10.0 * math.log10(mse)
+
+
+def render_view_sharded(nerf, H, W, c2w, bounds, intrinsic, process_group=None, dst=0, rays=None):
+    """One view marched by ALL ranks of `process_group`: rank r takes the contiguous ray range
+    dist.shard_range(H*W, r, G), replicated weights, no communication on the data path; the only collective is the final
+    gather of the image rows. Returns, on rank `dst` (every rank when dst is None), the device tensor [H*W, 5] fp32 =
+    (r, g, b, depth, acc) of the fine model; None elsewhere. `rays` = this rank's shard (rays_o, rays_d, near, far)
+    when the rays are already resident; otherwise the get_rays kernel generates exactly the shard. The Philox streams
+    are keyed by the global ray id, so the image does not depend on G."""
+    import torch.distributed as tdist
+    world = tdist.get_world_size(process_group) if (tdist.is_available() and tdist.is_initialized()) else 1
+    rank = tdist.get_rank(process_group) if world > 1 else 0
+    a, b = nbdist.shard_range(H * W, rank, world)
+    dev = nerf.device
+    if rays is None:
+        ro, rd = ray_utils.get_rays(H, W, intrinsic, c2w, a, b - a, device=dev)
+        near = torch.full((b - a, 1), float(np.float32(bounds[0])), device=dev)
+        far = torch.full((b - a, 1), float(np.float32(bounds[1])), device=dev)
+    else:
+        ro, rd, near, far = rays
+        assert ro.shape[0] == b - a, "rays must be this rank's shard_range of the view"
+    _, fine = nerf.render_rays(ro, rd, near, far, ray0=a, need_weights=False, keep_coarse=False)
+    rows = torch.cat([fine["pred_rgb"], fine["pred_depth"].reshape(-1, 1), fine["acc_map"].reshape(-1, 1)], dim=1)
+    if world == 1:
+        return rows
+    return nbdist.gather_rows(rows, H * W, process_group, dst)
+
+
+def predict_view_sharded(nerf, ds_host_shard, n_total, process_group=None, dst=0):
+    """End-to-end form of render_view_sharded for HOST rays: `ds_host_shard` is a RayDataset over this rank's
+    shard_range of the view's rays in host memory (NumPy). NeRF.predict stages them to the device through pinned
+    buffers and marches them; the fine model's (rgb, depth, acc) rows are gathered to rank `dst` and copied to the host
+    there. Returns the [n_total, 5] NumPy array on `dst`, None elsewhere."""
+    import torch.distributed as tdist
+    world = tdist.get_world_size(process_group) if (tdist.is_available() and tdist.is_initialized()) else 1
+    _, fine = nerf.predict(ds_host_shard, return_weights=False, as_numpy=False)
+    rows = torch.cat([fine["pred_rgb"], fine["pred_depth"].reshape(-1, 1), fine["acc_map"].reshape(-1, 1)], dim=1)
+    full = rows if world == 1 else nbdist.gather_rows(rows, n_total, process_group, dst)
+    if full is None:
+        return None
+    pin = nerf._ws.get(("pin_rows", n_total))
+    if pin is None:
+        pin = nerf._ws[("pin_rows", n_total)] = torch.empty((n_total, 5), dtype=torch.float32).pin_memory()
+    pin.copy_(full, non_blocking=True)
+    torch.cuda.current_stream(nerf.device).synchronize()
+    return pin.numpy()
+
+
+def evaluate_views(nerf, H, W, poses, bounds, intrinsic, gts_u8, scale_factor=None, process_group=None, depth_maps=False):
     """eval.py-shaped test-set loop (BASELINE config 4): renders every view, returns per-view PSNRs and
     their mean. Views are dealt round-robin to the ranks of `process_group` (no collective on the data
     path; the PSNR values are gathered at the end). Note: the reference logs np.mean(psnr) -- the LAST
@@ -75,11 +127,12 @@ def evaluate_views(nerf, H, W, poses, bounds, intrinsic, gts_u8, scale_factor=No
     local = torch.zeros(len(poses), device=nerf.device, dtype=torch.float64)
     for i in mine:
         b = bounds[i] if np.ndim(bounds) == 2 else bounds
-        r = render_view(nerf, H, W, poses[i], b, intrinsic, gt_u8=gts_u8[i], scale_factor=scale_factor, depth_maps=False)
-        local[i] = r["psnr"]
+        r = render_view(nerf, H, W, poses[i], b, intrinsic, gt_u8=gts_u8[i], scale_factor=scale_factor, depth_maps=depth_maps,
+                        lazy_psnr=True)
+        local[i:i + 1].copy_(r["sq_err"])          # stays on the device: no host sync between views
     if world > 1:
-        tdist.all_reduce(local, group=process_group)
-    vals = local.cpu().numpy()
+        tdist.all_reduce(local, group=process_group)      # the job's only collective: 8 bytes per view
+    vals = np.array([psnr_from_sq_err(float(v), H * W) for v in local.cpu().numpy()], dtype=np.float64)
     return {"psnr_vals": vals, "mean_psnr": float(vals.mean()), "last_view_psnr": float(vals[-1])}
 
 

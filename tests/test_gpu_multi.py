@@ -1,0 +1,106 @@
+"""GPU, 2 ranks over NCCL (skipped with fewer than 2 GPUs): the multi-GPU semantics of SURVEY.md 8e.
+
+  * a ray-sharded render (contiguous ray range per rank, final gather of the image rows) equals the single-GPU render
+    BIT FOR BIT -- rays are independent units and the Philox streams are keyed by the global ray id;
+  * a data-parallel train_step (batch split over the ranks, one all-reduce of the flat gradient/loss buffer, replicated
+    fused Adam; the reference's single-device semantics are core/model.py:148-171) leaves the same parameters as the
+    single-GPU step on the whole batch, to fp32 summation order.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _scene(H, W):
+    import nerf_tf2_b200 as nb
+    return nb.scene.SyntheticScene(H, W, num_cameras=4)
+
+
+def _worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import nerf_tf2_b200 as nb
+    from nerf_tf2_b200 import render as nbrender
+    res = {}
+    H, W = 60, 44                                           # 2640 rays: the two shards straddle tiles and chunks unevenly
+    sc = _scene(H, W)
+    for prec in ("bf16", "tf32"):
+        nerf = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision=prec, seed=3, rng_seed=5,
+                              render_chunk=1000)
+        rows = nbrender.render_view_sharded(nerf, H, W, sc.poses[1], sc.bounds, sc.K, dst=0)
+        if rank == 0:
+            res[f"render_{prec}"] = rows.cpu().numpy()
+        else:
+            assert rows is None
+    # data-parallel training step on this rank's half of a 512-ray batch
+    B = 512
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, H * W, (B,), generator=g, dtype=torch.int32)
+    rgb = torch.rand((B, 3), generator=g)
+    for prec in ("fp32", "bf16"):
+        tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision="bf16", train_precision=prec,
+                            seed=4, rng_seed=9)
+        tn.set_distributed()
+        lo, hi = nb.dist.shard_range(B, rank, world)
+        ro, rd = nb.ray_utils.get_rays_at(H, W, sc.K, sc.poses[0], ids[lo:hi].cuda())
+        near = torch.full((hi - lo, 1), sc.near, device="cuda"); far = torch.full((hi - lo, 1), sc.far, device="cuda")
+        for _ in range(2):
+            tn.train_step(((ro, rd, near, far), (rgb[lo:hi].cuda(),)))
+        res[f"params_{prec}_{rank}"] = tn.flat_params.cpu().numpy()
+        res[f"loss_{prec}_{rank}"] = float(tn.last_loss.item())
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_sharded_render_and_data_parallel_step_equal_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import nerf_tf2_b200 as nb
+    from nerf_tf2_b200 import render as nbrender
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    H, W = 60, 44
+    sc = _scene(H, W)
+    torch.cuda.set_device(0)
+    for prec in ("bf16", "tf32"):
+        nerf = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision=prec, seed=3, rng_seed=5,
+                              render_chunk=1000)
+        full = nbrender.render_view_sharded(nerf, H, W, sc.poses[1], sc.bounds, sc.K).cpu().numpy()
+        assert full.shape == (H * W, 5)
+        assert np.array_equal(full, r0[f"render_{prec}"]), prec                 # bit for bit
+    B = 512
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, H * W, (B,), generator=g, dtype=torch.int32)
+    rgb = torch.rand((B, 3), generator=g)
+    for prec in ("fp32", "bf16"):
+        tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision="bf16", train_precision=prec,
+                            seed=4, rng_seed=9)
+        ro, rd = nb.ray_utils.get_rays_at(H, W, sc.K, sc.poses[0], ids.cuda())
+        near = torch.full((B, 1), sc.near, device="cuda"); far = torch.full((B, 1), sc.far, device="cuda")
+        for _ in range(2):
+            tn.train_step(((ro, rd, near, far), (rgb.cuda(),)))
+        p1 = tn.flat_params.cpu().numpy()
+        assert np.array_equal(r0[f"params_{prec}_0"], r1[f"params_{prec}_1"]), prec    # replicas stay identical
+        # lr = 5e-4: two Adam steps move a weight by up to 1e-3; the data-parallel result agrees to 2e-6
+        assert np.abs(p1 - r0[f"params_{prec}_0"]).max() <= 2e-6, (prec, np.abs(p1 - r0[f"params_{prec}_0"]).max())
+        assert abs(float(tn.last_loss.item()) - r0[f"loss_{prec}_0"]) <= 1e-5 * abs(r0[f"loss_{prec}_0"])
