@@ -237,7 +237,7 @@ def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_
         tso = torch.empty((B, S), device="cuda")
 
         def run(x):
-            check(lib.nerfb200_sample_fine(B, Nc, Nf, ptr(x[0]), ptr(x[1]), ptr(x[2]), ptr(x[3], allow_none=True), 1, 0,
+            check(lib.nerfb200_sample_fine(B, Nc, Nf, ptr(x[0]), ptr(x[1]), ptr(x[2]), ptr(x[3], allow_none=True), 1, None, 0,
                                            ptr(tso), None, None, None, st), "sample_fine")
         ms = timed(run, data)
         results.append({"key": key, "kernel": name, "rays": B, "Nc": Nc, "Nf": Nf, "bytes_per_ray": bpr, "us": ms * 1e3,
@@ -249,7 +249,7 @@ def hbm_kernels_alone(rays=65536, iters=20, warmup=5, sets=0, nc=N_COARSE, nf=N_
     outs = [(torch.empty((B, Nc), device="cuda"), torch.empty((B, Nc + 1), device="cuda")) for _ in range(nsets(B * bpr))]
 
     def run(x):
-        check(lib.nerfb200_sample_coarse(B, Nc, 1, 1, ptr(near), ptr(far), None, 1, 0, ptr(x[0]), ptr(x[1]), st), "sample_coarse")
+        check(lib.nerfb200_sample_coarse(B, Nc, 1, 1, ptr(near), ptr(far), None, 1, None, 0, ptr(x[0]), ptr(x[1]), st), "sample_coarse")
     ms = timed(run, outs)
     results.append({"key": "sample_coarse", "kernel": "sample_coarse_kernel (in-kernel uniforms, 1/t spacing)", "rays": B, "Nc": Nc,
                     "bytes_per_ray": bpr, "us": ms * 1e3, "GBps": B * bpr / (ms / 1e3) / 1e9, "input_sets": len(outs)})
@@ -570,30 +570,42 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
     rgb = torch.rand((Bl, 3), device=dev)
     p = nb.make_params({"system": {"white_bg": True}})
     tp = args.train_precision
-    tn = nb.setup_model(p, precision=tp if tp != "fp32" else "bf16", train_precision=tp, seed=0)
-    if world > 1:
-        tn.set_distributed()
     batch = ((ro, rd, near, far), (rgb,))
     steps = 50
-    for _ in range(5):
-        tn.train_step(batch)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        tn.train_step(batch)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        ms = nb.dist.max_over_ranks(ms, dev)
+
+    def run(graph):
+        tn = nb.setup_model(p, precision=tp if tp != "fp32" else "bf16", train_precision=tp, seed=0, cuda_graph=graph,
+                            precise_last=False)
+        if world > 1:
+            tn.set_distributed()
+        for _ in range(5):
+            tn.train_step(batch)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            tn.train_step(batch)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            ms = nb.dist.max_over_ranks(ms, dev)
+        captured = any("graph" in st for st in tn._graphs.values())
+        del tn
+        return ms, captured
+
+    ms_eager, _ = run(False)
+    ms, captured = run(True) if not args.no_train_graph else (ms_eager, False)
     sps = steps / (ms / 1e3)
     flop = 3489024 * B * ROWS_PER_RAY
     pk = peaks()
     return {"metric": "train steps/s (4096-ray batch, coarse+fine fwd/bwd + Adam, data-parallel all-reduce)",
             "value": sps, "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "precision": tp,
             "global_batch": B, "rays_per_gpu": Bl, "achieved_tflops": flop * sps / 1e12,
-            "frac_of_sustained_peak": flop * sps / 1e12 / (pk["tensor"] * world)}
+            "frac_of_sustained_peak": flop * sps / 1e12 / (pk["tensor"] * world),
+            "launch_mode": "one CUDA graph per step (sampling, forwards, loss, backwards, all-reduce, Adam, repack)" if captured
+                           else "eager launches",
+            "eager": {"value": steps / (ms_eager / 1e3), "ms_per_step": ms_eager / steps}}
 
 
 def main():
@@ -612,6 +624,7 @@ def main():
     ap.add_argument("--no-hbm", action="store_true", help="skip the stand-alone timings of the HBM-bound kernels")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg4 / cfg5 sub-workloads and the return_weights=True leg")
     ap.add_argument("--cfg4-views", type=int, default=200)
+    ap.add_argument("--no-train-graph", action="store_true", help="time the training step with eager launches only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 1
+#define NERFB200_ABI_VERSION 2
 
 #define NERFB200_EINVAL   10001   /* bad argument                      */
 #define NERFB200_ENOTSUP  10002   /* shape outside the supported range */
@@ -87,8 +87,12 @@ NERFB200_API int nerfb200_get_rays_at(int H, int W, const float* K, const float*
  * perturb==0: bin mid-points (with the bin_widths fix of SURVEY.md App. B1).
  * Outputs t_vals[B,Nc], bin_edges[B,Nc+1] (left = [:, :-1], right = [:, 1:]). */
 NERFB200_API int nerfb200_sample_coarse(int64_t B, int Nc, int lin_inv_depth, int perturb, const float* near,
-                           const float* far, const float* u_coarse, uint64_t seed, int64_t ray0,
-                           float* t_vals, float* bin_edges, void* stream);
+                           const float* far, const float* u_coarse, uint64_t seed, const int64_t* step_state,
+                           int64_t ray0, float* t_vals, float* bin_edges, void* stream);
+/* `step_state` (may be NULL) -- device-resident step state int64[2] = {optimizer iterations, sampling step}: when given,
+ * the samplers use seed ^ step_state[1] and nerfb200_adam_step reads the iteration count from step_state[0], so that a
+ * whole training step captured in a CUDA graph advances its noise and its learning-rate schedule on replay
+ * (nerfb200_step_advance increments both counters on the stream). */
 
 /* xyz/dir network inputs exactly as the reference materialises them (utils/ray_utils.py:251-258):
  * xyz = o + t*d (separate multiply and add), dirs broadcast. For parity tests and the FP32
@@ -186,7 +190,7 @@ NERFB200_API int nerfb200_composite_bwd(int64_t B, int S, const float* sigma, co
  * {32,64,128,256,512}. */
 NERFB200_API int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights,
                          const float* bin_edges, const float* t_coarse, const float* u_fine,
-                         uint64_t seed, int64_t ray0, float* t_sorted /* [B,Nc+Nf] */,
+                         uint64_t seed, const int64_t* step_state, int64_t ray0, float* t_sorted /* [B,Nc+Nf] */,
                          int32_t* piece_idxs, float* cdf, float* t_fine, void* stream);
 
 /* ---- a12: loss + optimiser -----------------------------------------------------------------
@@ -199,7 +203,8 @@ NERFB200_API int nerfb200_mse_loss_grad(int64_t B, int64_t B_global, const float
  * (core/model.py:413-418); `iterations` is the counter BEFORE the step. Fused over the flat
  * parameter block. */
 NERFB200_API int nerfb200_adam_step(int64_t n, float* params, const float* grads, float* m, float* v,
-                       int64_t iterations, void* stream);
+                       int64_t iterations, const int64_t* step_state /* overrides `iterations` when non-NULL */, void* stream);
+NERFB200_API int nerfb200_step_advance(int64_t* step_state /* device int64[2] */, void* stream);
 
 /* ---- a15: depth map type_2 (utils/ray_utils.py:122-130) -------------------------------------
  * z of the point o + d*depth/scale in the camera frame. */

@@ -31,7 +31,7 @@ SIGNATURES = {
     "nerfb200_get_rays": (_i32, [_i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _i64, _i64, _vp, _vp, _vp]),
     "nerfb200_get_rays_f32": (_i32, [_i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _i64, _i64, _vp, _vp, _vp]),
     "nerfb200_get_rays_at": (_i32, [_i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _i64, _vp, _vp, _vp]),
-    "nerfb200_sample_coarse": (_i32, [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _i64, _vp, _vp, _vp]),
+    "nerfb200_sample_coarse": (_i32, [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _i64, _vp, _vp, _vp]),
     "nerfb200_make_inputs": (_i32, [_i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_positional_encode": (_i32, [_i64, _i32, _vp, _vp, _vp]),
     "nerfb200_create": (_i32, [C.POINTER(_vp)]),
@@ -46,9 +46,10 @@ SIGNATURES = {
     "nerfb200_mlp_backward_weights": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp]),
     "nerfb200_composite_fwd": (_i32, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_composite_bwd": (_i32, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
-    "nerfb200_sample_fine": (_i32, [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _u64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "nerfb200_sample_fine": (_i32, [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _u64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_mse_loss_grad": (_i32, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "nerfb200_adam_step": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "nerfb200_adam_step": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nerfb200_step_advance": (_i32, [_vp, _vp]),
     "nerfb200_depth_type2": (_i32, [_i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _dbl, _vp, _vp, _vp]),
     "nerfb200_sample_pixels": (_i32, [_i64, _i64, _u64, _u64, _vp, _vp]),
     "nerfb200_gather_rgb_u8": (_i32, [_i64, _vp, _vp, _vp, _vp]),

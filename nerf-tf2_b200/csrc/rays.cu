@@ -107,7 +107,9 @@ __device__ __forceinline__ float bin_edge(float near, float far, int k, int Nc, 
 // bin_edge() above, in the same order: bit-identical to the one-thread-per-edge form.
 __global__ void sample_coarse_kernel(int64_t B, int Nc, int lin_inv, int perturb, const float* __restrict__ near,
                                      const float* __restrict__ far, const float* __restrict__ u_in, uint64_t seed,
-                                     int64_t ray0, float* __restrict__ t_vals, float* __restrict__ edges) {
+                                     const int64_t* __restrict__ step_dev, int64_t ray0, float* __restrict__ t_vals,
+                                     float* __restrict__ edges) {
+    if (step_dev) seed ^= (uint64_t)__ldg(step_dev + 1);      // device-resident step counter (CUDA-graph replays)
     const int G = (Nc + 3) >> 2;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * G) return;
@@ -307,13 +309,13 @@ int nerfb200_get_rays_at(int H, int W, const float* K, const float* c2w, const i
 }
 
 int nerfb200_sample_coarse(int64_t B, int Nc, int lin_inv_depth, int perturb, const float* near, const float* far,
-                           const float* u_coarse, uint64_t seed, int64_t ray0, float* t_vals, float* bin_edges,
-                           void* stream) {
+                           const float* u_coarse, uint64_t seed, const int64_t* step_state, int64_t ray0, float* t_vals,
+                           float* bin_edges, void* stream) {
     NB_CHECK_ARG(B >= 0 && Nc >= 2, "sample_coarse: bad shape");
     if (B == 0) return 0;
     NB_CHECK_ARG(near && far && t_vals && bin_edges, "sample_coarse: NULL pointer");
     sample_coarse_kernel<<<blocks_for(B * ((Nc + 3) / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-        B, Nc, lin_inv_depth, perturb, near, far, u_coarse, seed, ray0, t_vals, bin_edges);
+        B, Nc, lin_inv_depth, perturb, near, far, u_coarse, seed, step_state, ray0, t_vals, bin_edges);
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -80,9 +80,11 @@ __device__ __forceinline__ void warp_bitonic_sort(float (&v)[EF], int lane) {
 template <int EF>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_fine_kernel(int64_t B, int Nc, const float* __restrict__ bin_weights, const float* __restrict__ bin_edges,
-                   const float* __restrict__ t_coarse, const float* __restrict__ u_fine, uint64_t seed, int64_t ray0,
+                   const float* __restrict__ t_coarse, const float* __restrict__ u_fine, uint64_t seed,
+                   const int64_t* __restrict__ step_dev, int64_t ray0,
                    float* __restrict__ t_sorted, int32_t* __restrict__ piece_idxs, float* __restrict__ cdf_out,
                    float* __restrict__ t_fine_out) {
+    if (step_dev) seed ^= (uint64_t)__ldg(step_dev + 1);      // device-resident step counter (CUDA-graph replays)
     constexpr int Nf = 32 * EF;
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,8 +261,9 @@ template <int NC, int NF, bool SORTED>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_fine_fast_kernel(int64_t B, const float* __restrict__ bin_weights, const float* __restrict__ bin_edges,
                         const float* __restrict__ t_coarse, const float* __restrict__ u_fine, uint64_t seed,
-                        int64_t ray0, float* __restrict__ t_sorted, int32_t* __restrict__ piece_idxs,
-                        float* __restrict__ cdf_out, float* __restrict__ t_fine_out) {
+                        const int64_t* __restrict__ step_dev, int64_t ray0, float* __restrict__ t_sorted,
+                        int32_t* __restrict__ piece_idxs, float* __restrict__ cdf_out, float* __restrict__ t_fine_out) {
+    if (step_dev) seed ^= (uint64_t)__ldg(step_dev + 1);      // device-resident step counter (CUDA-graph replays)
     static_assert((NC & (NC - 1)) == 0 && NC >= 32, "fast path: N_coarse must be a power of two");
     static_assert((NF & (NF - 1)) == 0 && NF >= 128, "fast path: N_fine must be a power of two >= 128");
     constexpr int EC = NC / 32, EF = NF / 32, S = NC + NF, ES = S / 32;
@@ -580,8 +583,8 @@ using namespace nb;
 extern "C" {
 
 int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights, const float* bin_edges,
-                         const float* t_coarse, const float* u_fine, uint64_t seed, int64_t ray0, float* t_sorted,
-                         int32_t* piece_idxs, float* cdf, float* t_fine, void* stream) {
+                         const float* t_coarse, const float* u_fine, uint64_t seed, const int64_t* step_state, int64_t ray0,
+                         float* t_sorted, int32_t* piece_idxs, float* cdf, float* t_fine, void* stream) {
     NB_CHECK_ARG(B >= 0, "sample_fine: negative ray count");
     if (!(Nc >= 32 && Nc <= 256 && Nc % 32 == 0)) {
         set_error("sample_fine: N_coarse must be a multiple of 32 in [32,256], got %d", Nc);
@@ -601,7 +604,7 @@ int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights, co
         unsigned g = (unsigned)((B + kSamplerWarps - 1) / kSamplerWarps);
 #define NB_LAUNCH_FAST(NCv, NFv, SRT)                                                                                   \
     sample_fine_fast_kernel<NCv, NFv, SRT><<<g, kSamplerWarps * 32, 0, st>>>(B, bin_weights, bin_edges, t_coarse, u_fine, \
-                                                                             seed, ray0, t_sorted, piece_idxs, cdf, t_fine)
+                                                                             seed, step_state, ray0, t_sorted, piece_idxs, cdf, t_fine)
         if (Nc == 64) {
             if (u_fine) NB_LAUNCH_FAST(64, 128, false); else NB_LAUNCH_FAST(64, 128, true);
         } else {
@@ -621,7 +624,7 @@ int nerfb200_sample_fine(int64_t B, int Nc, int Nf, const float* bin_weights, co
             NB_CUDA(cudaFuncSetAttribute(sample_fine_kernel<EFv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                          \
         sample_fine_kernel<EFv><<<grid, kSamplerWarps * 32, smem, st>>>(B, Nc, bin_weights, bin_edges, t_coarse, \
-                                                                         u_fine, seed, ray0, t_sorted, piece_idxs, \
+                                                                         u_fine, seed, step_state, ray0, t_sorted, piece_idxs, \
                                                                          cdf, t_fine);                        \
     } while (0)
     switch (Nf / 32) {

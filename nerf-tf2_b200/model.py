@@ -171,12 +171,16 @@ class _Adam:
                 arr = torch.as_tensor(np.asarray(weights[1 + k * len(vs) + i]), dtype=torch.float32)
                 buf[var._ofs:var._ofs + var._n].copy_(arr.reshape(-1))
 
-    def apply_gradients(self, flat_grads):
+    def apply_gradients(self, flat_grads, step_state=None):
+        """One fused Adam launch over the flat parameter block. `step_state` (device int64[2]): the iteration count is
+        read on the device (CUDA-graph replays); the caller then advances both the device and the host counter."""
         n = self._nerf.flat_params.numel()
         with torch.cuda.device(self._nerf.device):
             check(load().nerfb200_adam_step(n, ptr(self._nerf.flat_params), ptr(flat_grads), ptr(self.m), ptr(self.v),
-                                            self.iterations, stream_ptr()), "adam_step")
-        self.iterations += 1
+                                            self.iterations, ptr(step_state, torch.int64, allow_none=True), stream_ptr()),
+                  "adam_step")
+        if step_state is None:
+            self.iterations += 1
         self._nerf._dirty = True
 
 
@@ -190,7 +194,7 @@ class NeRF:
     """NeRF(Model) (core/model.py:18-287)."""
 
     def __init__(self, params, precision="bf16", train_precision=None, seed=0, device=None,
-                 rng_seed=0, render_chunk=32768, precise_last=True):
+                 rng_seed=0, render_chunk=32768, precise_last=True, cuda_graph=False):
         """`precision`: MLP arithmetic of forward/predict -- "bf16" (default), "fp16", "tf32" (tcgen05 tensor cores,
         fp32 accumulate) or "fp32" (CUDA-core check path). `train_precision` defaults to `precision` (bf16 for a
         tf32 model: tf32 is a render precision). `precise_last`: the tensor-core forwards recompute sigma of every
@@ -253,6 +257,8 @@ class NeRF:
         self.process_group = None
         self.world_size, self.rank = 1, 0
         self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
+        self.use_cuda_graph = bool(int(cuda_graph))     # train_step as one CUDA graph per batch shape (after two eager steps)
+        self._graphs, self._step_dev, self._step_dev_host = {}, None, None
         self._step_counter = 0
         self.last_loss = None
 
@@ -349,7 +355,7 @@ class NeRF:
     # ---------------------------------------------------------------------------- the ray march
     @_on_device
     def forward(self, rays_o, rays_d, near, far, u_coarse=None, u_fine=None, ray0=0, precision=None,
-                need_weights=True, _train=None):
+                need_weights=True, _train=None, _step_state=None):
         """NeRF.forward (core/model.py:57-125): stratified sampling -> coarse MLP -> compositing ->
         hierarchical sampling -> fine MLP -> compositing. Returns (post_proc_CM, post_proc_FM).
         `u_coarse`/`u_fine` are the fixed uniforms of the parity contract; when None the kernels
@@ -357,8 +363,11 @@ class NeRF:
         s = self.params.sampling
         precision = self.precision if precision is None else precision
         rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
-        seed = (self.rng_seed << 20) ^ self._step_counter
-        t_c, edges = ray_utils.sample_coarse(s.N_coarse, s.lin_inv_depth, s.perturb, near, far, u_coarse, seed, ray0)
+        # the sampling noise is keyed by (rng_seed, step, global ray id); with a device-resident step state the step is
+        # XORed in on the device, so that a captured step draws fresh noise at every replay
+        seed = (self.rng_seed << 20) ^ (self._step_counter if _step_state is None else 0)
+        t_c, edges = ray_utils.sample_coarse(s.N_coarse, s.lin_inv_depth, s.perturb, near, far, u_coarse, seed, ray0,
+                                             step_state=_step_state)
         st_c = st_f = None
         if _train is not None:
             R_c, R_f = t_c.shape[0] * s.N_coarse, t_c.shape[0] * (s.N_coarse + s.N_fine)
@@ -366,7 +375,7 @@ class NeRF:
             st_f = self._scratch("stash_f", load().nerfb200_mlp_stash_bytes(R_f, precision))
         rgb_c, sig_c = self._mlp(COARSE, rays_o, rays_d, t_c, precision, st_c)
         pp_c = ray_utils.post_process_model_output(rgb_c, sig_c, t_c, self.white_bg)
-        t_f = ray_utils.sample_fine(s.N_fine, pp_c["weights"], edges, t_c, u_fine, seed, ray0)
+        t_f = ray_utils.sample_fine(s.N_fine, pp_c["weights"], edges, t_c, u_fine, seed, ray0, step_state=_step_state)
         rgb_f, sig_f = self._mlp(FINE, rays_o, rays_d, t_f, precision, st_f)
         pp_f = ray_utils.post_process_model_output(rgb_f, sig_f, t_f, self.white_bg, need_weights=need_weights)
         if _train is not None:
@@ -390,14 +399,15 @@ class NeRF:
 
     # -------------------------------------------------------------------------------- training
     def _loss_and_grads(self, rays_o, rays_d, near, far, rgb, u_coarse=None, u_fine=None, ray0=0,
-                        global_batch=None, coarse_done=None):
+                        global_batch=None, coarse_done=None, step_state=None):
         """Forward + backward of train_step (core/model.py:148-170) into self.flat_grads (local sum).
         Returns the device tensor [loss] (this rank's share of the global mean losses)."""
         prec = self.train_precision
         B = rays_o.shape[0]
         Bg = B * self.world_size if global_batch is None else global_batch
         tr = {}
-        pp_c, pp_f = self.forward(rays_o, rays_d, near, far, u_coarse, u_fine, ray0, precision=prec, _train=tr)
+        pp_c, pp_f = self.forward(rays_o, rays_d, near, far, u_coarse, u_fine, ray0, precision=prec, _train=tr,
+                                  _step_state=step_state)
         self._grad_buf.zero_()                       # the kernels accumulate into the gradient and the loss
         loss = self._grad_buf[PARAMS_TOTAL:PARAMS_TOTAL + 1]
         d_c = torch.empty((B, 3), device=self.device, dtype=torch.float32)
@@ -460,6 +470,9 @@ class NeRF:
         ro, rd, near, far, rgb = (self._to_device(a) for a in (ro, rd, near, far, rgb))
         if ray0 is None:
             ray0 = self.rank * int(ro.shape[0])
+        if self.use_cuda_graph and u_coarse is None and u_fine is None and self._dw_overlap_sms <= 0:
+            if self._train_step_graphed(ro, rd, near, far, rgb, ray0):
+                return {m.name: m.result_async() for m in self.metrics}
         pending = []
         coarse_done = None
         if self.world_size > 1 and self.overlap_allreduce:
@@ -482,6 +495,61 @@ class NeRF:
         self._step_counter += 1
         self.last_loss = loss
         return {m.name: m.result_async() for m in self.metrics}     # no device sync: see PSNRMetric.result_async
+
+    @_on_device
+    def _train_step_graphed(self, ro, rd, near, far, rgb, ray0):
+        """The whole step -- sampling, both forwards, loss, both backwards, the gradient all-reduce, Adam, the repack of
+        the operand images -- as ONE CUDA graph per batch shape: ~35 launches per step are otherwise issued one by
+        one from Python, which is what bounds a data-parallel step of 512 rays per GPU. The first two steps of a
+        shape run eagerly (they size every scratch buffer), the third is captured, later ones replay it. What changes
+        from step to step lives on the device: the input batch (copied into static buffers), the sampling step and
+        the optimizer iteration (`_step_dev`, advanced inside the graph). Returns False when the step must run eagerly."""
+        key = (int(ro.shape[0]), int(ray0))
+        st = self._graphs.setdefault(key, {"calls": 0})
+        st["calls"] += 1
+        if st.get("failed") or st["calls"] <= 2:
+            return False
+        lib = load()
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self._step_dev_host = None
+        want = (int(self.optimizer.iterations), int(self._step_counter))
+        if self._step_dev_host != want:                       # eager steps ran in between: re-seed the device counters
+            self._step_dev.copy_(torch.tensor(want, dtype=torch.int64))
+            self._step_dev_host = want
+        if "graph" not in st:
+            static = [torch.empty_like(x) for x in (ro, rd, near, far, rgb)]
+            self._sync_packed(self.train_precision)
+            for m in self.metrics:
+                m._ensure(self.device)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    self._loss_and_grads(*static, ray0=ray0, step_state=self._step_dev)
+                    if self.world_size > 1:
+                        import torch.distributed as dist
+                        dist.all_reduce(self._grad_buf, group=self.process_group)     # ONE collective: gradient + loss
+                    self.optimizer.apply_gradients(self.flat_grads, step_state=self._step_dev)
+                    check(lib.nerfb200_step_advance(ptr(self._step_dev, torch.int64), stream_ptr()), "step_advance")
+                    check(lib.nerfb200_pack_weights(self._ctx, ptr(self.flat_params), stream_ptr()), "pack_weights")
+            except Exception as ex:       # e.g. a collective that cannot be captured: stay eager, loudly
+                import warnings
+                warnings.warn(f"CUDA-graph capture of train_step failed ({ex}); continuing with eager launches")
+                st["failed"] = True
+                torch.cuda.synchronize(self.device)
+                return False
+            st["graph"], st["static"] = g, static
+        for dst, src in zip(st["static"], (ro, rd, near, far, rgb)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        st["graph"].replay()
+        self.optimizer.iterations += 1
+        self._step_counter += 1
+        self._step_dev_host = (int(self.optimizer.iterations), int(self._step_counter))
+        self._dirty = False                                   # the graph repacked the operand images after Adam
+        self.last_loss = self._grad_buf[PARAMS_TOTAL:PARAMS_TOTAL + 1]
+        return True
 
     @_on_device
     def test_step(self, data, u_coarse=None, u_fine=None, ray0=0):

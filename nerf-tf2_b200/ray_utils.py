@@ -82,15 +82,17 @@ def create_depth_map(pred_depth, H, W, scale_factor, map_type, intrinsic=None, C
     raise ValueError(f"Invalid map_type: {map_type}")
 
 
-def sample_coarse(N_coarse, lin_inv_depth, perturb, near, far, u_vals=None, seed=0, ray0=0):
-    """Kernel-level stratified sampler: returns (t_vals[B,Nc], bin_edges[B,Nc+1])."""
+def sample_coarse(N_coarse, lin_inv_depth, perturb, near, far, u_vals=None, seed=0, ray0=0, step_state=None):
+    """Kernel-level stratified sampler: returns (t_vals[B,Nc], bin_edges[B,Nc+1]). `step_state`: optional device
+    int64[2] whose second entry is XORed into the seed on the device (CUDA-graph replays, include/nerfb200.h)."""
     near = near.reshape(-1).contiguous()
     far = far.reshape(-1).contiguous()
     B = near.shape[0]
     t = torch.empty((B, N_coarse), device=near.device, dtype=torch.float32)
     edges = torch.empty((B, N_coarse + 1), device=near.device, dtype=torch.float32)
     check(load().nerfb200_sample_coarse(B, N_coarse, int(bool(lin_inv_depth)), int(bool(perturb)), ptr(near),
-                                        ptr(far), ptr(u_vals, allow_none=True), seed, ray0, ptr(t), ptr(edges),
+                                        ptr(far), ptr(u_vals, allow_none=True), seed,
+                                        ptr(step_state, torch.int64, allow_none=True), ray0, ptr(t), ptr(edges),
                                         stream_ptr()), "sample_coarse")
     return t, edges
 
@@ -129,7 +131,7 @@ def create_input_batch_coarse_model(params, rays_o, rays_d, near, far, u_vals=No
     return data
 
 
-def sample_fine(N_fine, bin_weights, bin_edges, t_vals_coarse, u_vals=None, seed=0, ray0=0, debug=False):
+def sample_fine(N_fine, bin_weights, bin_edges, t_vals_coarse, u_vals=None, seed=0, ray0=0, debug=False, step_state=None):
     """Kernel-level hierarchical sampler. Returns t_sorted[B,Nc+Nf] (and, with debug=True, a dict
     with piece_idxs, the fp32 cdf the indices were searched in, and the unsorted t_fine)."""
     B, Nc = bin_weights.shape
@@ -141,8 +143,8 @@ def sample_fine(N_fine, bin_weights, bin_edges, t_vals_coarse, u_vals=None, seed
         cdf = torch.empty((B, Nc + 1), device=dev, dtype=torch.float32)
         tf = torch.empty((B, N_fine), device=dev, dtype=torch.float32)
     check(load().nerfb200_sample_fine(B, Nc, N_fine, ptr(bin_weights.contiguous()), ptr(bin_edges.contiguous()),
-                                      ptr(t_vals_coarse.contiguous()), ptr(u_vals, allow_none=True), seed, ray0,
-                                      ptr(t_sorted), ptr(idx, torch.int32, allow_none=True),
+                                      ptr(t_vals_coarse.contiguous()), ptr(u_vals, allow_none=True), seed,
+                                      ptr(step_state, torch.int64, allow_none=True), ray0, ptr(t_sorted), ptr(idx, torch.int32, allow_none=True),
                                       ptr(cdf, allow_none=True), ptr(tf, allow_none=True), stream_ptr()),
           "sample_fine")
     if debug:

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_param_layout():
     lib = _lib.load()
-    assert lib.nerfb200_abi_version() == 1
+    assert lib.nerfb200_abi_version() == 2
     offs = _lib.param_offsets()
     assert offs[0] == 0 and offs[1] == 63 * 256 and offs[-1] == _lib.PARAMS_PER_MODEL == 595844
     from oracle import model as om
@@ -45,8 +45,8 @@ def test_argument_validation_needs_no_gpu():
     # all of these fail argument checks before any CUDA call
     assert lib.nerfb200_composite_fwd(4, 1, None, None, None, 0, None, None, None, None, None) == 10001
     assert b"S" in lib.nerfb200_last_error()
-    assert lib.nerfb200_sample_fine(4, 48, 128, 1, 1, 1, None, 0, 0, 1, None, None, None, None) == 10002
-    assert lib.nerfb200_sample_fine(4, 64, 100, 1, 1, 1, None, 0, 0, 1, None, None, None, None) == 10002
+    assert lib.nerfb200_sample_fine(4, 48, 128, 1, 1, 1, None, 0, None, 0, 1, None, None, None, None) == 10002
+    assert lib.nerfb200_sample_fine(4, 64, 100, 1, 1, 1, None, 0, None, 0, 1, None, None, None, None) == 10002
     assert lib.nerfb200_mlp_forward(None, 0, 1, 1, None, None, None, None, None, None, 1, None, None, None) == 10001
     assert lib.nerfb200_get_rays(0, 4, None, None, 0, 0, None, None, None) == 10001
     # the phase-split backward validates like mlp_backward: no context -> EINVAL, before any CUDA call

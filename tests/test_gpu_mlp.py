@@ -295,3 +295,35 @@ def test_context_is_bound_to_its_device():
         rgb, sig = nerf.coarse_model((x, dv_))          # current device stays 0: the model enters its own device
         outs.append((rgb.cpu(), sig.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_graphed_train_step_equals_eager(precision):
+    """train_step captured as ONE CUDA graph (device-resident step state: sampling step and Adam iteration advance
+    inside the graph) leaves bit-identical parameters, optimizer state, loss and metric as the eager launches, with the
+    in-kernel sampling noise ON (so a replay that reused the captured step's noise or learning rate would differ)."""
+    H = W = 32
+    v = osc.synthetic_view(H, W, view=0)
+    rng = np.random.default_rng(0)
+    gt = rng.random((H * W, 3), dtype=F32)
+    batches = [tuple(dev(v[k][s0:s0 + 256]) for k in ("rays_o", "rays_d", "near", "far")) + (dev(gt[s0:s0 + 256]),)
+               for s0 in (0, 256, 512)]
+    finals = []
+    for graph in (False, True):
+        nerf = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision="bf16",
+                              train_precision=precision, seed=2, rng_seed=7, cuda_graph=graph)
+        logs = None
+        for i in range(7):
+            b = batches[i % 3]
+            logs = nerf.train_step(((b[0], b[1], b[2], b[3]), (b[4],)))
+        torch.cuda.synchronize()
+        if graph:
+            assert any("graph" in st for st in nerf._graphs.values()), "the step was never captured"
+        finals.append((nerf.flat_params.clone(), nerf.optimizer.m.clone(), nerf.optimizer.v.clone(), float(nerf.last_loss.item()),
+                       float(logs["psnr_metric"]), nerf.optimizer.iterations))
+    (p0, m0, v0, l0, q0, it0), (p1, m1, v1, l1, q1, it1) = finals
+    assert it0 == it1 == 7
+    assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+    assert l0 == l1 and q0 == q1
+    # and the operand images were repacked inside the graph: a render right after uses the new weights
+    assert nerf._dirty is False
