@@ -410,7 +410,8 @@ def run_b200(args):
              "us_per_launch": alone["sample_fine"]["us"], "in_step_GBps": in_step["sample_fine"], "launches": sf_n,
              "share_of_step": sf_ms / ms_b},
             {"kernel": alone["sample_coarse"]["kernel"], "bound": "hbm", "achieved": alone["sample_coarse"]["GBps"], "peak": pk["hbm"],
-             "unit": "GB/s", "frac": alone["sample_coarse"]["GBps"] / pk["hbm"], "traffic": None,
+             "unit": "GB/s", "frac": alone["sample_coarse"]["GBps"] / pk["hbm"],
+             "traffic": ncu_traffic(NCU_HBM_CSV, "sample_coarse_kernel")[0], "traffic_source": src_h,
              "us_per_launch": alone["sample_coarse"]["us"], "in_step_GBps": in_step["sample_coarse"], "launches": sc_n,
              "share_of_step": sc_ms / ms_b},
         ]
@@ -465,6 +466,14 @@ def run_b200(args):
         del ds_host, host
     barrier()
 
+    # ---- secondary metric: 4096-ray training step (coarse+fine fwd/bwd + Adam [+ all-reduce])
+    train = None
+    if not args.no_train:
+        try:
+            train = bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args)
+        except Exception as ex:  # report, do not hide
+            train = {"error": str(ex)[:300]}
+
     # ---- named sub-workloads: BASELINE.json configs[3] and configs[4]
     workloads = {}
     if not args.no_extra:
@@ -477,14 +486,6 @@ def run_b200(args):
         except Exception as ex:
             workloads["cfg5_1080p_128_256"] = {"error": str(ex)[:300]}
     barrier()
-
-    # ---- secondary metric: 4096-ray training step (coarse+fine fwd/bwd + Adam [+ all-reduce])
-    train = None
-    if not args.no_train:
-        try:
-            train = bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args)
-        except Exception as ex:  # report, do not hide
-            train = {"error": str(ex)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

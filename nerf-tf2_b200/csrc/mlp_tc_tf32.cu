@@ -348,18 +348,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                 const uint32_t tcols = tmem_lane + (uint32_t)(buf * 256);
                 const float* bias = s_heads + head_bias(j);
                 if (j < 10) {
-                    // N = 256: this group drains columns [128 grp, 128 grp + 128) = activation chunks 4 grp .. 4 grp + 3;
-                    // dense_9 (N = 128): columns [64 grp, 64 grp + 64) = chunks 2 grp, 2 grp + 1
+                    // The two groups take the 32-column chunks ALTERNATELY (group g: chunks g, g + 2, g + 4, ...), so that
+                    // chunks become ready in the order the next layer's MMAs consume them, two at a time: with each
+                    // group owning one contiguous half, chunk 1 was ready only after chunk 0 AND 1 of the same warps
+                    // while chunks 4.. sat finished and unused. N = 256: 4 chunks per group; dense_9 (N = 128): 2.
                     const int nch = j == 9 ? 2 : 4;
-                    const int ch0 = grp * nch;
                     uint32_t r[2][32];
-                    tmem_ld32(tcols + 32u * ch0, r[0]);
+                    tmem_ld32(tcols + 32u * grp, r[0]);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (c < nch) {
-                            const int ch = ch0 + c;
+                            const int ch = grp + 2 * c;
                             tmem_ld_wait(r[c & 1]);
-                            if (c + 1 < nch) tmem_ld32(tcols + 32u * (ch + 1), r[(c + 1) & 1]);
+                            if (c + 1 < nch) tmem_ld32(tcols + 32u * (ch + 2), r[(c + 1) & 1]);
                             if (j == 7) drain32<true, true>(r[c & 1], bias + 32 * ch, act + ch * kChunk, row, wsig + 32 * ch, sg);
                             else if (j == 8) drain32<false, false>(r[c & 1], bias + 32 * ch, act + ch * kChunk, row, wsig, sg);
                             else drain32<true, false>(r[c & 1], bias + 32 * ch, act + ch * kChunk, row, wsig, sg);
