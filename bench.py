@@ -376,7 +376,9 @@ def run_b200(args):
     # near/far read, t [B,Nc] and bin edges [B,Nc+1] written; u generated in-kernel
     sc_bytes = args.steps * my_rays * (8 + 4 * N_COARSE + 4 * (N_COARSE + 1))
     mlp_kernel = "mlp_tf32_forward_kernel" if args.precision == "tf32" else "mlp_tc_forward_pair_kernel"
-    traffic, traffic_src = ncu_traffic(NCU_MLP_CSV.get(args.precision, ""), mlp_kernel)
+    # (the main launch, not the small split launch whose name differs in the last template argument only)
+    traffic, traffic_src = ncu_traffic(NCU_MLP_CSV.get(args.precision, ""),
+                                       mlp_kernel if args.precision == "tf32" else "mlp_tc_forward_pair_kernel<0, 0, 0, 0>")
     roofline = {"bound": "tensor",
                 "kernel": f"{mlp_kernel} (fused encoding + 8x256 MLP on tcgen05 cta_group::2; coarse, fine and split last-sample launches)",
                 "achieved": mlp_tflops, "peak": tensor_peak, "unit": "TFLOP/s", "frac": mlp_tflops / tensor_peak,

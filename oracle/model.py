@@ -76,8 +76,11 @@ def positional_encode(x, L):
     return torch.cat([x, sincos], dim=-1)
 
 
-def mlp_forward(w, model_name, xyz, dirs):
-    """get_coarse_or_fine_model forward (core/model.py:334-394). w: name -> torch tensor."""
+def mlp_forward(w, model_name, xyz, dirs, return_pre=False):
+    """get_coarse_or_fine_model forward (core/model.py:334-394). w: name -> torch tensor. `return_pre` also returns
+    the sigma head's pre-activation (the reference applies ReLU to it, core/model.py:375): the distance of the LAST
+    sample's pre-activation from zero says how well conditioned a ray's output is (delta_last = 1e10,
+    utils/ray_utils.py:459-468: alpha_last is 0 or 1 according to its sign)."""
     def dense(name, h):
         return h @ w[f"{model_name}/{name}/kernel"] + w[f"{model_name}/{name}/bias"]
 
@@ -88,11 +91,14 @@ def mlp_forward(w, model_name, xyz, dirs):
         h = torch.relu(dense(f"dense_{i}", h))
         if i == 4:
             h = torch.cat([h, enc_xyz], dim=-1)
-    sigma = torch.relu(dense("sigma", h))
+    sigma_pre = dense("sigma", h)
+    sigma = torch.relu(sigma_pre)
     bott = dense("dense_8", h)
     g = torch.cat([bott, enc_dir], dim=-1)
     g = torch.relu(dense("dense_9", g))
     rgb = torch.sigmoid(dense("rgb", g))
+    if return_pre:
+        return rgb, sigma, sigma_pre
     return rgb, sigma
 
 
@@ -106,17 +112,20 @@ def to_torch(w, dtype=torch.float32, requires_grad=False):
     return out
 
 
-def mlp_forward_np(w_np, model_name, xyz, dirs, dtype=torch.float32, chunk=1 << 16):
+def mlp_forward_np(w_np, model_name, xyz, dirs, dtype=torch.float32, chunk=1 << 16, return_pre=False):
     """NumPy-in / NumPy-out chunked forward (no grad)."""
     w = to_torch(w_np, dtype)
-    rgbs, sigmas = [], []
+    rgbs, sigmas, pres = [], [], []
     with torch.no_grad():
         for s in range(0, xyz.shape[0], chunk):
-            r, sg = mlp_forward(w, model_name,
-                                torch.from_numpy(np.ascontiguousarray(xyz[s:s + chunk])).to(dtype),
-                                torch.from_numpy(np.ascontiguousarray(dirs[s:s + chunk])).to(dtype))
+            r, sg, pre = mlp_forward(w, model_name,
+                                     torch.from_numpy(np.ascontiguousarray(xyz[s:s + chunk])).to(dtype),
+                                     torch.from_numpy(np.ascontiguousarray(dirs[s:s + chunk])).to(dtype), return_pre=True)
             rgbs.append(r.to(torch.float32).numpy())
             sigmas.append(sg.to(torch.float32).numpy())
+            pres.append(pre.to(torch.float32).numpy())
+    if return_pre:
+        return np.concatenate(rgbs, 0), np.concatenate(sigmas, 0), np.concatenate(pres, 0)
     return np.concatenate(rgbs, 0), np.concatenate(sigmas, 0)
 
 
@@ -126,17 +135,20 @@ def forward(w_np, rays_o, rays_d, near, far, N_coarse=64, N_fine=128, lin_inv_de
     """NeRF.forward (core/model.py:57-125) with explicit uniforms."""
     d_cm = rm.create_input_batch_coarse_model(N_coarse, lin_inv_depth, perturb, rays_o, rays_d,
                                               near, far, u_coarse)
-    rgb_c, sig_c = mlp_forward_np(w_np, "coarse", d_cm["xyz_inputs"], d_cm["dir_inputs"], mlp_dtype)
+    rgb_c, sig_c, pre_c = mlp_forward_np(w_np, "coarse", d_cm["xyz_inputs"], d_cm["dir_inputs"], mlp_dtype, return_pre=True)
     pp_c = rm.post_process_model_output(rgb_c, sig_c, d_cm["t_vals"], white_bg)
     d_fm = rm.create_input_batch_fine_model(rays_o, rays_d, pp_c["weights"], d_cm["bin_data"],
                                             d_cm["t_vals"], u_fine, return_debug=True)
-    rgb_f, sig_f = mlp_forward_np(w_np, "fine", d_fm["xyz_inputs"], d_fm["dir_inputs"], mlp_dtype)
+    rgb_f, sig_f, pre_f = mlp_forward_np(w_np, "fine", d_fm["xyz_inputs"], d_fm["dir_inputs"], mlp_dtype, return_pre=True)
     pp_f = rm.post_process_model_output(rgb_f, sig_f, d_fm["t_vals"], white_bg)
     if return_debug:
         dbg = {"t_coarse": d_cm["t_vals"], "t_fine_sorted": d_fm["t_vals"],
                "rgb_c": rgb_c, "sigma_c": sig_c, "rgb_f": rgb_f, "sigma_f": sig_f,
                "cdf": d_fm["cdf"], "piece_idxs": d_fm["piece_idxs"],
-               "bin_edges": d_cm["bin_data"]["bin_edges"]}
+               "bin_edges": d_cm["bin_data"]["bin_edges"],
+               # pre-activation of the sigma head at the LAST sample of every ray, coarse and fine
+               "sigma_pre_last_c": pre_c.reshape(d_cm["t_vals"].shape)[:, -1].copy(),
+               "sigma_pre_last_f": pre_f.reshape(d_fm["t_vals"].shape)[:, -1].copy()}
         return pp_c, pp_f, dbg
     return pp_c, pp_f
 

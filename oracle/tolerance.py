@@ -1,0 +1,60 @@
+"""
+TEST INFRASTRUCTURE ONLY -- the stated per-pixel tolerance of the tensor-core renders against the fp32 oracle, in one
+place (tests/, __graft_entry__.smoke() and tools/ use it).
+
+Form of the statement (BASELINE.json north_star: "rendered RGB/depth/acc within a stated per-pixel absolute tolerance"):
+for rgb, depth (W3 units, near/far 0.425/1.275) and acc, coarse and fine output alike,
+
+    p99 over all pixels <= p99 bound,   and   EVERY pixel <= max bound,
+
+except pixels of rays whose LAST sample's alpha differs from the oracle's. The reference sets delta_last = 1e10
+(utils/ray_utils.py:459-468), so alpha_last is exactly 0 or 1 according to the SIGN of the last sample's sigma
+pre-activation: the reference's output is a discontinuous function there, and no finite-precision implementation
+(another BLAS, TF32 on the reference's own GPU path) reproduces the side of the jump for rays that sit on it. Two
+things can move a ray across:
+  (1) rounding of that row's MLP evaluation -- removed here by the split-operand launch over the last-sample rows
+      (without it: ~0.2 % of rays with bf16 operands, measured, profiles/r2a_parity_diag.json);
+  (2) for the fine network, the POSITION of the last sample: it is usually a hierarchical sample, i.e. a function of
+      the coarse network's weights, and a random-init network with 2^9*pi positional frequencies changes its sigma
+      pre-activation by up to ~3e-2 when that position moves by the ~1e-3 the 16-bit coarse pass moves it.
+Class (2) remains; the check below COUNTS such rays (they are identified by the flipped alpha_last itself, read from
+the `weights` outputs: w_last = T_last * alpha_last) and bounds their rate at 0.05 % (measured: 1 in ~12 000 rays).
+"""
+import numpy as np
+
+# precision -> (p99 bound, max bound) per output, PSNR-vs-structured-GT bound in dB
+RENDER_TOL = {
+    "bf16": dict(pred_rgb=(4e-3, 1.5e-2), pred_depth=(8e-3, 4e-2), acc_map=(5e-3, 2e-2), psnr=0.05),
+    "fp16": dict(pred_rgb=(2e-3, 1.2e-2), pred_depth=(3e-3, 3e-2), acc_map=(2e-3, 1.5e-2), psnr=0.02),
+    "tf32": dict(pred_rgb=(2e-3, 1.2e-2), pred_depth=(3e-3, 3e-2), acc_map=(2e-3, 1.5e-2), psnr=0.02),
+}
+MAX_FLIP_RATE = 5e-4
+
+
+def last_alpha_flips(gpu_c, gpu_f, ref_c, ref_f):
+    """Boolean [n]: rays whose last-sample alpha (0 or 1) differs from the oracle's, coarse or fine. Only rays whose
+    transmittance reaches the last sample can show it (w_last = T_last * alpha_last)."""
+    f = np.zeros(ref_f["weights"].shape[0], dtype=bool)
+    for g, r in ((gpu_c, ref_c), (gpu_f, ref_f)):
+        f |= (np.asarray(g["weights"])[:, -1] > 0) != (np.asarray(r["weights"])[:, -1] > 0)
+    return f
+
+
+def check_render(precision, gpu_c, gpu_f, ref_c, ref_f, max_flip_rate=MAX_FLIP_RATE):
+    """Asserts the stated tolerance; returns the measured values. Dicts hold NumPy arrays with keys pred_rgb [n,3],
+    pred_depth [n], acc_map [n], weights [n,S]."""
+    tol = RENDER_TOL[precision]
+    n = ref_f["pred_rgb"].shape[0]
+    flips = last_alpha_flips(gpu_c, gpu_f, ref_c, ref_f)
+    meas = {"n": int(n), "last_alpha_flips": int(flips.sum())}
+    allowed = max(1, int(np.floor(max_flip_rate * n)))      # a tiny view may hold one such ray
+    assert flips.sum() <= allowed, f"{precision}: {int(flips.sum())} rays with a flipped last-sample alpha of {n} (allowed {allowed})"
+    for name, g, r in (("coarse", gpu_c, ref_c), ("fine", gpu_f, ref_f)):
+        for key in ("pred_rgb", "pred_depth", "acc_map"):
+            e = np.abs(np.asarray(g[key]).reshape(n, -1) - np.asarray(r[key]).reshape(n, -1)).max(axis=1)
+            ok = e[~flips] if name == "fine" else e[~flips]
+            p99, mx = float(np.percentile(e, 99)), float(ok.max()) if ok.size else 0.0
+            meas[f"{name}_{key}"] = {"p99": p99, "max_over_unflipped": mx, "max_over_all": float(e.max())}
+            assert p99 <= tol[key][0], (precision, name, key, "p99", p99, tol[key][0])
+            assert mx <= tol[key][1], (precision, name, key, "max", mx, tol[key][1])
+    return meas

