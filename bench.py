@@ -512,7 +512,14 @@ def run_b200(args):
                 "gpu_launches": int(launches_timed), "clocks": clk, "weak": weak, "workloads": workloads, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave without tearing the communicator down: every rank has passed the last collective (barrier), the line is
+        # out, and ncclCommDestroy at interpreter exit is where multi-rank jobs hang when anything still holds NCCL work
+        import gc
+        gc.collect()
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def bench_cfg4(nb, nbrender, nerf, torch, dist, world, rank, barrier, max_ranks, args):
@@ -594,6 +601,7 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
         if world > 1:
             ms = nb.dist.max_over_ranks(ms, dev)
         captured = any("graph" in st for st in tn._graphs.values())
+        tn.release_cuda_graphs()      # captured NCCL work must be gone before the process group is torn down
         del tn
         return ms, captured
 

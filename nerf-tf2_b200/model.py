@@ -551,6 +551,15 @@ class NeRF:
         self.last_loss = self._grad_buf[PARAMS_TOTAL:PARAMS_TOTAL + 1]
         return True
 
+    def release_cuda_graphs(self):
+        """Drops the captured training-step graphs (they hold their private memory pool and, data-parallel, captured NCCL
+        work: release them before destroying the process group)."""
+        torch.cuda.synchronize(self.device)
+        self._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(self.device)
+
     @_on_device
     def test_step(self, data, u_coarse=None, u_fine=None, ray0=0):
         """NeRF.test_step (core/model.py:182-223): forward + metric update on the fine output."""
