@@ -101,6 +101,9 @@ def test_two_rank_sharded_render_and_data_parallel_step_equal_single_gpu():
             tn.train_step(((ro, rd, near, far), (rgb.cuda(),)))
         p1 = tn.flat_params.cpu().numpy()
         assert np.array_equal(r0[f"params_{prec}_0"], r1[f"params_{prec}_1"]), prec    # replicas stay identical
-        # lr = 5e-4: two Adam steps move a weight by up to 1e-3; the data-parallel result agrees to 2e-6
-        assert np.abs(p1 - r0[f"params_{prec}_0"]).max() <= 2e-6, (prec, np.abs(p1 - r0[f"params_{prec}_0"]).max())
+        # lr = 5e-4: two Adam steps move a weight by up to 1e-3; the data-parallel result agrees to 2e-6 with the fp32
+        # kernels and to 2e-5 with the bf16 tensor-core kernels (measured 6.5e-6: the weight-gradient GEMM sums the rows
+        # of a different tile grouping, and Adam's g / sqrt(v) amplifies fp32 summation-order noise of near-zero gradients)
+        lim = 2e-6 if prec == "fp32" else 2e-5
+        assert np.abs(p1 - r0[f"params_{prec}_0"]).max() <= lim, (prec, np.abs(p1 - r0[f"params_{prec}_0"]).max())
         assert abs(float(tn.last_loss.item()) - r0[f"loss_{prec}_0"]) <= 1e-5 * abs(r0[f"loss_{prec}_0"])
