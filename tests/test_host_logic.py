@@ -116,3 +116,52 @@ def test_metric_value_is_a_lazy_number():
     assert (v + 1) - 1 == pytest.approx(ref) and 2 * v == pytest.approx(2 * ref) and -v == -ref
     assert json.dumps({"psnr": float(v)}) == json.dumps({"psnr": ref})
     assert m.result() != ref
+
+
+def test_render_tolerance_statement():
+    """oracle/tolerance.py: p99 + bounded maximum over every pixel; only rays whose last-sample alpha flipped are exempt,
+    and only up to the stated rate."""
+    from oracle.tolerance import MAX_FLIP_RATE, RENDER_TOL, check_render, last_alpha_flips
+    rng = np.random.default_rng(0)
+    n = 4000
+
+    def outputs(S):
+        w = rng.random((n, S), dtype=np.float32) * 0.01 + 1e-3
+        return {"pred_rgb": rng.random((n, 3), dtype=np.float32), "pred_depth": rng.random(n, dtype=np.float32),
+                "acc_map": rng.random(n, dtype=np.float32), "weights": w}
+    ref_c, ref_f = outputs(64), outputs(192)
+    copy = lambda d: {k: v.copy() for k, v in d.items()}
+    g_c, g_f = copy(ref_c), copy(ref_f)
+    g_f["pred_rgb"] += 1e-3
+    m = check_render("bf16", g_c, g_f, ref_c, ref_f)
+    assert m["last_alpha_flips"] == 0 and abs(m["fine_pred_rgb"]["max_over_all"] - 1e-3) < 1e-6
+    # one pixel beyond the maximum, last-sample alpha unchanged: not exempt
+    bad = copy(g_f); bad["pred_rgb"][7, 1] += 0.3
+    with pytest.raises(AssertionError):
+        check_render("bf16", g_c, bad, ref_c, ref_f)
+    # the same pixel with a flipped last-sample alpha (w_last 0 <-> >0) is the counted exception ...
+    flip = copy(bad); flip["weights"][7, -1] = 0.0
+    assert last_alpha_flips(g_c, flip, ref_c, ref_f).sum() == 1
+    assert check_render("bf16", g_c, flip, ref_c, ref_f)["last_alpha_flips"] == 1
+    # ... but only up to the stated rate
+    many = copy(flip); many["weights"][:10, -1] = 0.0
+    assert MAX_FLIP_RATE * n < 10
+    with pytest.raises(AssertionError):
+        check_render("bf16", g_c, many, ref_c, ref_f)
+    assert RENDER_TOL["fp16"]["pred_rgb"][1] < RENDER_TOL["bf16"]["pred_rgb"][1]
+
+
+def test_bench_reads_traffic_from_the_committed_ncu_exports():
+    """roofline.traffic is parsed from the `ncu --page raw --csv` exports under profiles/ that the line names."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    t, src = bench.ncu_traffic(bench.NCU_MLP_CSV["bf16"], "mlp_tc_forward_pair_kernel<0, 0, 0, 0>")
+    assert src.startswith("profiles/") and 1.5e8 < t < 3.0e8          # ~200 MB per fine launch (50 MB read + 147 MB written)
+    t32, _ = bench.ncu_traffic(bench.NCU_MLP_CSV["tf32"], "mlp_tf32_forward_kernel")
+    assert 1.5e8 < t32 < 3.0e8
+    th, _ = bench.ncu_traffic(bench.NCU_HBM_CSV, "sample_fine_fast_kernel")
+    assert 3e7 < th < 1.2e8
+    assert bench.ncu_traffic("no_such_file.csv", "x") == (None, None)
+    assert bench.ncu_traffic(bench.NCU_HBM_CSV, "no_such_kernel") == (None, None)
