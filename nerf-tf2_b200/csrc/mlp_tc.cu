@@ -122,8 +122,8 @@ template <> __device__ __forceinline__ __half to16<__half>(float v) { return __f
 
 // One thread per 16-byte unit of the packed image.
 template <typename T, bool kLo>
-__global__ void pack_weights_kernel(const float* __restrict__ P /* one model */, uint8_t* __restrict__ img, int nchunks) {
-    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_weights_unit(const float* __restrict__ P /* one model */, uint8_t* __restrict__ img, int nchunks,
+                                                  int64_t u) {
     // locate chunk by linear scan over the table (<= 80 entries)
     int ci = -1;
     uint32_t byte = (uint32_t)(u * 16);
@@ -165,9 +165,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ P /* one model */,
 // cycles per layer: as many bytes into registers as the accumulator itself; tools/epi_probe.cu). K-major, no swizzle:
 // N-row i of the CTA's share is the 16 bytes [hi, lo, 0, 0, 0, 0, 0, 0] with hi + lo = bias to ~2^-17 relative.
 template <typename T>
-__global__ void pack_bias_tiles_kernel(const float* __restrict__ P /* one model */, uint8_t* __restrict__ tiles) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (job, rank, row)
-    if (i >= kNumJobs * 2 * 128) return;
+__device__ __forceinline__ void pack_bias_tile_row(const float* __restrict__ P /* one model */, uint8_t* __restrict__ tiles, int i) {
+    if (i >= kNumJobs * 2 * 128) return;                          // i = (job, rank, row)
     const int job = i / 256, rank = (i >> 7) & 1, row = i & 127;
     const int job_layer[kNumJobs] = {L0, L1, L2, L3, L4, L5, L6, L7, L8, L9, LRGB};
     const int l = job_layer[job];
@@ -185,8 +184,7 @@ __global__ void pack_bias_tiles_kernel(const float* __restrict__ P /* one model 
     *reinterpret_cast<uint4*>(tiles + (size_t)(job * 2 + rank) * kBiasTileBytes + row * 16) = *reinterpret_cast<uint4*>(v);
 }
 
-__global__ void pack_heads_kernel(const float* __restrict__ P, float* __restrict__ hp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_heads_elem(const float* __restrict__ P, float* __restrict__ hp, int i) {
     if (i >= HeadOffsets::total) return;
     const int job_layer[kNumJobs] = {L0, L1, L2, L3, L4, L5, L6, L7, L8, L9, LRGB};
     float v = 0.f;
@@ -201,6 +199,34 @@ __global__ void pack_heads_kernel(const float* __restrict__ P, float* __restrict
         v = P[bias_offset(LSIGMA)];
     }
     hp[i] = v;
+}
+
+// ONE launch packs everything the forward kernels of one precision read, for both models (blockIdx.y): the operand image
+// (hi), optionally the lo image of the split launch, the bias tiles and the fp32 head block -- a training step repacks
+// after every Adam update, and at 512 rays per GPU ten separate 3-10 us launches were 5 % of a data-parallel step.
+struct PackParams {
+    const float* P;              // flat parameters, coarse then fine
+    uint8_t* img[2];             // operand image per model (bias tiles behind the chunks)
+    uint8_t* img_lo[2];          // lo image per model, or NULL
+    float* heads[2];
+    uint32_t bias_ofs;
+    int nchunks;
+    int blocks_w, blocks_b, blocks_h;      // 256-thread blocks per section; sections: hi [, lo], bias tiles, heads
+};
+template <typename T>
+__global__ void pack_images_kernel(const PackParams pp) {
+    const int m = blockIdx.y;
+    const float* P = pp.P + (int64_t)m * kParamsPerModel;
+    int b = blockIdx.x;
+    if (b < pp.blocks_w) { pack_weights_unit<T, false>(P, pp.img[m], pp.nchunks, (int64_t)b * blockDim.x + threadIdx.x); return; }
+    b -= pp.blocks_w;
+    if (pp.img_lo[m]) {
+        if (b < pp.blocks_w) { pack_weights_unit<T, true>(P, pp.img_lo[m], pp.nchunks, (int64_t)b * blockDim.x + threadIdx.x); return; }
+        b -= pp.blocks_w;
+    }
+    if (b < pp.blocks_b) { pack_bias_tile_row<T>(P, pp.img[m] + pp.bias_ofs, b * blockDim.x + threadIdx.x); return; }
+    b -= pp.blocks_b;
+    pack_heads_elem(P, pp.heads[m], b * blockDim.x + threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -876,45 +902,45 @@ void tc_destroy(nerfb200_ctx* ctx) {
 }
 
 // Packs the operand images of the precisions in ctx->pack_mask (bit 0 bf16, bit 1 fp16, bit 2 tf32; a training loop
-// that uses one precision sets the mask and saves the other images' launches every step).
+// that uses one precision sets the mask and saves the other images' launches every step): one launch per 16-bit precision
+// for both models (pack_images_kernel) + one for the W^T images of backward-data (mlp_tc_train.cu).
 int tc_pack_weights(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st) {
     int rc = check_device(ctx, "pack_weights");
     if (rc) return rc;
     const ChunkTable& t = chunk_table();
-    const int64_t units = t.bias_ofs / 16;
-    const unsigned grid = (unsigned)((units + 255) / 256), bgrid = (kNumJobs * 256 + 255) / 256;
-    for (int m = 0; m < 2; ++m) {
-        const float* P = flat_params + (int64_t)m * kParamsPerModel;
-        if (ctx->pack_mask & 1) {
-            pack_weights_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m], t.n);
-            NB_LAUNCH_CHECK();
-            pack_bias_tiles_kernel<__nv_bfloat16><<<bgrid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m] + t.bias_ofs);
-            NB_LAUNCH_CHECK();
+    PackParams pp{};
+    pp.P = flat_params;
+    pp.bias_ofs = t.bias_ofs;
+    pp.nchunks = t.n;
+    pp.blocks_w = (int)((t.bias_ofs / 16 + 255) / 256);
+    pp.blocks_b = (kNumJobs * 256 + 255) / 256;
+    pp.blocks_h = (HeadOffsets::total + 255) / 256;
+    for (int m = 0; m < 2; ++m) pp.heads[m] = ctx->head_params[m];
+    // the split launch of a tf32 render uses the bf16 pair of images, so tf32 implies bf16 here
+    const bool want[2] = {(ctx->pack_mask & 1) || ((ctx->pack_mask & 4) && ctx->precise_last), (ctx->pack_mask & 2) != 0};
+    for (int pz = 0; pz < 2; ++pz) {
+        if (!want[pz]) continue;
+        for (int m = 0; m < 2; ++m) {
+            pp.img[m] = (uint8_t*)ctx->packed[pz][m];
+            pp.img_lo[m] = ctx->precise_last ? (uint8_t*)ctx->packed_lo[pz][m] : nullptr;
         }
-        if (ctx->pack_mask & 2) {
-            pack_weights_kernel<__half, false><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m], t.n);
-            NB_LAUNCH_CHECK();
-            pack_bias_tiles_kernel<__half><<<bgrid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[1][m] + t.bias_ofs);
-            NB_LAUNCH_CHECK();
-        }
-        if (ctx->precise_last) {   // lo images of the split launch (tf32 renders use the bf16 pair)
-            if (ctx->pack_mask & 5) { pack_weights_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed_lo[0][m], t.n); NB_LAUNCH_CHECK(); }
-            if (ctx->pack_mask & 2) { pack_weights_kernel<__half, true><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed_lo[1][m], t.n); NB_LAUNCH_CHECK(); }
-            if ((ctx->pack_mask & 5) == 4) {   // tf32 only: the split launch still needs the bf16 hi image
-                pack_weights_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m], t.n);
-                NB_LAUNCH_CHECK();
-                pack_bias_tiles_kernel<__nv_bfloat16><<<bgrid, 256, 0, st>>>(P, (uint8_t*)ctx->packed[0][m] + t.bias_ofs);
-                NB_LAUNCH_CHECK();
-            }
-        }
-        pack_heads_kernel<<<(HeadOffsets::total + 255) / 256, 256, 0, st>>>(P, ctx->head_params[m]);
+        const dim3 grid((unsigned)(pp.blocks_w * (ctx->precise_last ? 2 : 1) + pp.blocks_b + pp.blocks_h), 2);
+        if (pz == 0) pack_images_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(pp);
+        else pack_images_kernel<__half><<<grid, 256, 0, st>>>(pp);
+        NB_LAUNCH_CHECK();
+    }
+    if (!want[0] && !want[1]) {      // tf32 without the split launch: the fp32 head block is still needed
+        for (int m = 0; m < 2; ++m) { pp.img[m] = nullptr; pp.img_lo[m] = nullptr; }
+        PackParams ph = pp;
+        ph.blocks_w = 0; ph.blocks_b = 0;
+        pack_images_kernel<__nv_bfloat16><<<dim3((unsigned)ph.blocks_h, 2), 256, 0, st>>>(ph);
         NB_LAUNCH_CHECK();
     }
     if (ctx->pack_mask & 4) { rc = tf32_pack(ctx, flat_params, st); if (rc) return rc; }
     rc = tc_train_pack(ctx, flat_params, st);
     if (rc) return rc;
     ctx->packed_valid = true;
-    ctx->packed_mask = ctx->pack_mask;
+    ctx->packed_mask = ctx->pack_mask | (want[0] ? 1 : 0);
     ctx->packed_precise = ctx->precise_last;
     return 0;
 }

@@ -62,7 +62,10 @@ template <> __device__ __forceinline__ __nv_bfloat16 cvt16<__nv_bfloat16>(float 
 template <> __device__ __forceinline__ __half cvt16<__half>(float v) { return __float2half_rn(v); }
 
 template <typename T>
-__global__ void pack_bwd_weights_kernel(const float* __restrict__ P, uint8_t* __restrict__ img, int nchunks) {
+__global__ void pack_bwd_weights_kernel(const float* __restrict__ flat_params, uint8_t* __restrict__ img0, uint8_t* __restrict__ img1,
+                                        int nchunks) {
+    const float* P = flat_params + (int64_t)blockIdx.y * kParamsPerModel;      // blockIdx.y = model (coarse, fine)
+    uint8_t* img = blockIdx.y ? img1 : img0;
     int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= (int64_t)nchunks * (kChunkBytes / 16)) return;
     const int ci = (int)(u / (kChunkBytes / 16));
@@ -639,16 +642,14 @@ void tc_train_destroy(nerfb200_ctx* ctx) {
 int tc_train_pack(nerfb200_ctx* ctx, const float* flat_params, cudaStream_t st) {
     const BwdTable& t = bwd_table();
     const int64_t units = (int64_t)t.n * (kChunkBytes / 16);
-    for (int m = 0; m < 2; ++m) {
-        const float* P = flat_params + (int64_t)m * kParamsPerModel;
-        if (ctx->pack_mask & 1) {
-            pack_bwd_weights_kernel<__nv_bfloat16><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[0][m], t.n);
-            NB_LAUNCH_CHECK();
-        }
-        if (ctx->pack_mask & 2) {
-            pack_bwd_weights_kernel<__half><<<(unsigned)((units + 255) / 256), 256, 0, st>>>(P, (uint8_t*)ctx->packed_bwd[1][m], t.n);
-            NB_LAUNCH_CHECK();
-        }
+    const dim3 grid((unsigned)((units + 255) / 256), 2);          // both models in one launch
+    if (ctx->pack_mask & 1) {
+        pack_bwd_weights_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(flat_params, (uint8_t*)ctx->packed_bwd[0][0], (uint8_t*)ctx->packed_bwd[0][1], t.n);
+        NB_LAUNCH_CHECK();
+    }
+    if (ctx->pack_mask & 2) {
+        pack_bwd_weights_kernel<__half><<<grid, 256, 0, st>>>(flat_params, (uint8_t*)ctx->packed_bwd[1][0], (uint8_t*)ctx->packed_bwd[1][1], t.n);
+        NB_LAUNCH_CHECK();
     }
     return 0;
 }
