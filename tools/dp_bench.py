@@ -1,0 +1,58 @@
+"""Developer tool (torchrun, N GPUs): the data-parallel training step under different schedules --
+eager / CUDA graph, all-reduce of the coarse half overlapped with the fine backward or not, SMs reserved for NCCL.
+usage: torchrun --nproc-per-node N tools/dp_bench.py [steps]"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+import nerf_tf2_b200 as nb
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dev = torch.device("cuda", local)
+B = 4096 // world
+sc = nb.scene.SyntheticScene(800, 800)
+g = torch.Generator().manual_seed(rank)
+ids = torch.randint(0, 640000, (B,), generator=g, dtype=torch.int32).to(dev)
+ro, rd = nb.ray_utils.get_rays_at(800, 800, sc.K, sc.poses[0], ids)
+near = torch.full((B, 1), sc.near, device=dev); far = torch.full((B, 1), sc.far, device=dev)
+rgb = torch.rand((B, 3), device=dev)
+batch = ((ro, rd, near, far), (rgb,))
+res = {}
+for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserve=0)),
+                 ("eager_overlap", dict(graph=False, overlap=True, reserve=0)),
+                 ("eager_overlap_reserve4", dict(graph=False, overlap=True, reserve=4)),
+                 ("eager_overlap_reserve8", dict(graph=False, overlap=True, reserve=8)),
+                 ("eager_overlap_reserve16", dict(graph=False, overlap=True, reserve=16)),
+                 ("graph", dict(graph=True, overlap=False, reserve=0)),
+                 ("no_allreduce_graph", dict(graph=True, overlap=False, reserve=0, dist=False))):
+    tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}), precision="bf16", train_precision="bf16", cuda_graph=kw["graph"],
+                        precise_last=False)
+    if kw.get("dist", True):
+        tn.set_distributed()
+    tn.overlap_allreduce, tn.reserve_sms = kw["overlap"], kw["reserve"]
+    for _ in range(8):
+        tn.train_step(batch)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tn.train_step(batch)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = nb.dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    res[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms}
+    tn.release_cuda_graphs()
+    del tn
+if rank == 0:
+    print(json.dumps({"world": world, "rays_per_gpu": B, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "results": res}), flush=True)
+dist.barrier()
+sys.stdout.flush()
+os._exit(0)
