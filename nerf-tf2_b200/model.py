@@ -258,6 +258,7 @@ class NeRF:
         self.world_size, self.rank = 1, 0
         self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
         self.reserve_sms = 0              # ... on this many SMs that the fine backward's persistent kernels leave free
+        self.graph_overlap_allreduce = True   # the same fork/join inside a captured step
         self.use_cuda_graph = bool(int(cuda_graph))     # train_step as one CUDA graph per batch shape (after two eager steps)
         self._graphs, self._step_dev, self._step_dev_host = {}, None, None
         self._step_counter = 0
@@ -541,10 +542,21 @@ class NeRF:
             g = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(g):
-                    self._loss_and_grads(*static, ray0=ray0, step_state=self._step_dev)
+                    pending, coarse_done = [], None
+                    if self.world_size > 1 and self.overlap_allreduce and self.graph_overlap_allreduce:
+                        import torch.distributed as dist
+
+                        def coarse_done():      # a fork inside the capture: NCCL's stream joins again at the wait() below
+                            pending.append(dist.all_reduce(self._grad_buf[:PARAMS_PER_MODEL], group=self.process_group, async_op=True))
+                    self._loss_and_grads(*static, ray0=ray0, step_state=self._step_dev, coarse_done=coarse_done)
                     if self.world_size > 1:
                         import torch.distributed as dist
-                        dist.all_reduce(self._grad_buf, group=self.process_group)     # ONE collective: gradient + loss
+                        if pending:
+                            pending.append(dist.all_reduce(self._grad_buf[PARAMS_PER_MODEL:], group=self.process_group, async_op=True))
+                            for h in pending:
+                                h.wait()
+                        else:
+                            dist.all_reduce(self._grad_buf, group=self.process_group)     # ONE collective: gradient + loss
                     self.optimizer.apply_gradients(self.flat_grads, step_state=self._step_dev)
                     check(lib.nerfb200_step_advance(ptr(self._step_dev, torch.int64), stream_ptr()), "step_advance")
                     check(lib.nerfb200_pack_weights(self._ctx, ptr(self.flat_params), stream_ptr()), "pack_weights")

@@ -32,6 +32,7 @@ for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserv
                  ("eager_overlap_reserve8", dict(graph=False, overlap=True, reserve=8)),
                  ("eager_overlap_reserve16", dict(graph=False, overlap=True, reserve=16)),
                  ("graph", dict(graph=True, overlap=False, reserve=0)),
+                 ("graph_overlap", dict(graph=True, overlap=True, reserve=0)),
                  ("no_allreduce_graph", dict(graph=True, overlap=False, reserve=0, dist=False))):
     tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}), precision="bf16", train_precision="bf16", cuda_graph=kw["graph"],
                         precise_last=False)
@@ -40,6 +41,7 @@ for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserv
     tn.overlap_allreduce, tn.reserve_sms = kw["overlap"], kw["reserve"]
     for _ in range(8):
         tn.train_step(batch)
+    captured = any("graph" in st for st in tn._graphs.values())
     dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -48,7 +50,8 @@ for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserv
     e1.record()
     dist.barrier(); torch.cuda.synchronize()
     ms = nb.dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
-    res[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms}
+    res[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "captured": captured, "loss": float(tn.last_loss.item()),
+                 "param_sum": float(tn.flat_params.double().sum().item())}
     tn.release_cuda_graphs()
     del tn
 if rank == 0:
