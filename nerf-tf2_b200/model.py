@@ -257,7 +257,6 @@ class NeRF:
         self.process_group = None
         self.world_size, self.rank = 1, 0
         self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
-        self.reserve_sms = 0              # ... on this many SMs that the fine backward's persistent kernels leave free
         self.graph_overlap_allreduce = True   # the same fork/join inside a captured step
         self.use_cuda_graph = bool(int(cuda_graph))     # train_step as one CUDA graph per batch shape (after two eager steps)
         self._graphs, self._step_dev, self._step_dev_host = {}, None, None
@@ -430,20 +429,7 @@ class NeRF:
             if coarse_done is not None:
                 coarse_done()                        # data-parallel: the coarse half of the gradient is final
             ds_f, dr_f = ray_utils.composite_backward(tr["rgb_f"], tr["sig_f"], tr["t_f"], self.white_bg, d_f)
-            if coarse_done is not None and self.reserve_sms > 0 and prec != FP32:
-                # the fine model's backward leaves `reserve_sms` SMs to the all-reduce of the coarse half: the persistent
-                # kernels otherwise fill every SM (227 KB of shared memory per CTA) and NCCL's CTAs could only start at a
-                # kernel boundary, i.e. the collective would run between two kernels instead of next to them
-                Bf, Sf = tr["t_f"].shape
-                ws_f = self._scratch("mlp_bwd_ws", lib.nerfb200_mlp_workspace_bytes(Bf * Sf, prec, 1))
-                cap = self._num_sms - self.reserve_sms
-                check(lib.nerfb200_mlp_backward_data(self._ctx, FINE, Bf, Sf, ptr(self.flat_params), ptr(dr_f), ptr(ds_f), prec,
-                                                     ptr(ws_f, torch.uint8), ptr(tr["st_f"], torch.uint8), cap, stream_ptr()),
-                      "mlp_backward_data")
-                check(lib.nerfb200_mlp_backward_weights(self._ctx, FINE, Bf, Sf, ptr(self.flat_grads), prec, ptr(ws_f, torch.uint8),
-                                                        ptr(tr["st_f"], torch.uint8), cap, stream_ptr()), "mlp_backward_weights")
-            else:
-                self._mlp_backward(FINE, rays_o, rays_d, tr["t_f"], dr_f, ds_f, prec, tr["st_f"])
+            self._mlp_backward(FINE, rays_o, rays_d, tr["t_f"], dr_f, ds_f, prec, tr["st_f"])
             return loss, pp_c, pp_f
         # Phase-split backward. Per model: backward-data (writes the gradient stash: HBM-write bound), then the
         # weight-gradient GEMM (reads both stashes: HBM-read bound). The coarse model's weight-gradient phase runs on a

@@ -1,5 +1,6 @@
 """Developer tool (torchrun, N GPUs): the data-parallel training step under different schedules --
-eager / CUDA graph, all-reduce of the coarse half overlapped with the fine backward or not, SMs reserved for NCCL.
+eager / CUDA graph, all-reduce of the coarse half overlapped with the fine backward or not. (Leaving 4-16 SMs of the
+fine backward free for NCCL was measured too, profiles/r2k_dp_n8.json: no gain -- the option was removed again.)
 usage: torchrun --nproc-per-node N tools/dp_bench.py [steps]"""
 import json
 import os
@@ -28,9 +29,6 @@ batch = ((ro, rd, near, far), (rgb,))
 res = {}
 for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserve=0)),
                  ("eager_overlap", dict(graph=False, overlap=True, reserve=0)),
-                 ("eager_overlap_reserve4", dict(graph=False, overlap=True, reserve=4)),
-                 ("eager_overlap_reserve8", dict(graph=False, overlap=True, reserve=8)),
-                 ("eager_overlap_reserve16", dict(graph=False, overlap=True, reserve=16)),
                  ("graph", dict(graph=True, overlap=False, reserve=0)),
                  ("graph_overlap", dict(graph=True, overlap=True, reserve=0)),
                  ("no_allreduce_graph", dict(graph=True, overlap=False, reserve=0, dist=False))):
@@ -38,7 +36,7 @@ for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserv
                         precise_last=False)
     if kw.get("dist", True):
         tn.set_distributed()
-    tn.overlap_allreduce, tn.reserve_sms = kw["overlap"], kw["reserve"]
+    tn.overlap_allreduce = kw["overlap"]
     for _ in range(8):
         tn.train_step(batch)
     captured = any("graph" in st for st in tn._graphs.values())
