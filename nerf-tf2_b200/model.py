@@ -198,7 +198,8 @@ class NeRF:
         """`precision`: MLP arithmetic of forward/predict -- "bf16" (default), "fp16", "tf32" (tcgen05 tensor cores,
         fp32 accumulate) or "fp32" (CUDA-core check path). `train_precision` defaults to `precision` (bf16 for a
         tf32 model: tf32 is a render precision). `precise_last`: the tensor-core forwards recompute sigma of every
-        ray's last sample with split operands (NERFB200_OPT_PRECISE_LAST)."""
+        ray's last sample with split operands (NERFB200_OPT_PRECISE_LAST): True = render forwards (default),
+        "train" = training forwards too, False = never."""
         _lib.require_cuda()
         load()
         self.params = params
@@ -209,7 +210,8 @@ class NeRF:
         self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else precision
         tp = train_precision if train_precision is not None else ("bf16" if self.precision == TF32 else self.precision)
         self.train_precision = _lib.PRECISIONS[tp] if isinstance(tp, str) else tp
-        self.precise_last = bool(precise_last)
+        # False / True (render forwards) / "train" (training forwards too: NERFB200_OPT_PRECISE_LAST = 2)
+        self.precise_last = 2 if precise_last == "train" else int(bool(precise_last))
         self.rng_seed = rng_seed
         self.render_chunk = render_chunk
         self.val_cache = []

@@ -328,3 +328,26 @@ def test_graphed_train_step_equals_eager(precision):
         assert float(d.mean()) <= 2e-6 and float(d.max()) <= 7 * 2 * 5e-4 and abs(l0 - l1) <= 1e-4 * abs(l0) and abs(q0 - q1) <= 1e-2
     # and the operand images were repacked inside the graph: a render right after uses the new weights
     assert nerf._dirty is False
+
+
+def test_split_launch_in_training_forwards(golden):
+    """NERFB200_OPT_PRECISE_LAST = 2 (`precise_last="train"`): the training forward takes the split launch too; the
+    patched sigma also lands in the activation stash (the ReLU gate of the sigma head in backward-data reads it), so
+    loss and gradients stay consistent with each other and with the oracle."""
+    g = golden["oracle_forward_train"]
+    dv = lambda k: dev(g[k])
+    args = (dv("rays_o"), dv("rays_d"), dv("near"), dv("far"), dv("rgb_gt"))
+    out = {}
+    for mode in (True, "train"):
+        nerf = make_nerf(om.init_weights(7), "bf16", train_precision="bf16", precise_last=mode)
+        loss, pp_c, pp_f = nerf._loss_and_grads(*args, u_fine=dv("u_fine"))
+        torch.cuda.synchronize()
+        out[mode] = (float(loss.item()), nerf.flat_grads.double().clone(), pp_f["pred_rgb"].clone())
+        assert torch.isfinite(nerf.flat_grads).all()
+        assert abs(out[mode][0] - float(g["train_loss"])) <= 5e-3 * float(g["train_loss"])
+    # the rendered pixels of the training forward with the split launch equal the render forward's (same kernels + launch)
+    ref = make_nerf(om.init_weights(7), "bf16")
+    _, rf = ref.forward(dv("rays_o"), dv("rays_d"), dv("near"), dv("far"), u_fine=dv("u_fine"))
+    assert float((out["train"][2] - rf["pred_rgb"]).abs().max()) <= 1e-6
+    cos = float(torch.nn.functional.cosine_similarity(out[True][1], out["train"][1], dim=0))
+    assert cos >= 0.99, cos
