@@ -13,10 +13,13 @@
 //     the tensor pipe works on layer l+1 while layer l is still being drained. In place is safe: the epilogue of
 //     layer l starts after ALL of layer l's MMAs have completed (acc_full), i.e. after the last read of the buffer.
 // tf32 MMAs run at half the 16-bit rate (M=256, N=256, K=8 = 128 tensor cycles), so a layer is 32 instructions =
-// 4096 cycles of tensor work against ~1.2 k cycles of epilogue per SM sub-partition: the pipeline is tensor bound.
+// 4096 cycles of tensor work; what bounds the kernel is shared-memory bandwidth (every operand is twice as wide as in
+// the 16-bit kernel: >= 512 KB per layer and SM through a 128 B/clk pipe), so everything that can stay out of shared
+// memory does: the layer bias is added by the tensor core (a "ones" x bias-tile MMA starts each accumulator, as in
+// the pair kernel) and the sigma head's weights are read through L1.
 //
 // 2-CTA clusters, cta_group::2 (M = 256 = one tile per CTA), each CTA streams HALF of every weight chunk through
-// a 3 x 16 KB bulk-TMA ring; roles: warps 0-7 epilogue, warp 8 weight producer, warp 9 MMA issuer (leader CTA) /
+// a 4 x 16 KB bulk-TMA ring; roles: warps 0-7 epilogue, warp 8 weight producer, warp 9 MMA issuer (leader CTA) /
 // relay of "my half landed" (peer CTA).
 //
 // Jobs of one tile (K chunks of 32; issue order = encoding chunks first, they are ready long before):
@@ -35,23 +38,22 @@ namespace {
 
 constexpr int kJobs = 11;
 constexpr int kChunk = 16384;            // [128 rows x 32 K] fp32, 128 B per row, 16-byte units XOR-swizzled by (row & 7)
-constexpr int kStagesT = 3;
+constexpr int kStagesT = 4;
 constexpr int kSmemActT = 0;                               // 8 chunks = 128 KB
 constexpr int kSmemEncT = kSmemActT + 8 * kChunk;          // 2 chunks = 32 KB (enc_xyz; enc_dir re-uses chunk 0)
-constexpr int kSmemRingT = kSmemEncT + 2 * kChunk;         // 3 x 16 KB
+constexpr int kSmemRingT = kSmemEncT + 2 * kChunk;         // 4 x 16 KB
 constexpr int kSmemBarT = kSmemRingT + kStagesT * kChunk;
-constexpr int kHeadBias = 0;                               // fp32 side parameters staged in shared memory:
-constexpr int kHeadWsig = 9 * 256 + 128 + 16;              //   biases of jobs 0..8 (256 each), 9 (128), 10 (16), sigma kernel (256),
-constexpr int kHeadBsig = kHeadWsig + 256;                 //   sigma bias
-constexpr int kHeadTotal = kHeadBsig + 4;
-constexpr int kSmemHeadsT = kSmemBarT + 256;
-constexpr int kSmemSigT = kSmemHeadsT + kHeadTotal * 4;
+constexpr int kHeadWsig = 9 * 256 + 128 + 16;              // float offsets inside the fp32 head block (HeadOffsets of mlp_tc.cu):
+constexpr int kHeadBsig = kHeadWsig + 256;                 //   sigma kernel (256), sigma bias
+constexpr int kSmemOnesT = kSmemBarT + 256;                // 256 B "ones" A operand of the bias MMA step
+constexpr int kSmemBiasTileT = kSmemOnesT + 256;           // one job's bias tile (this CTA's N/2 rows x 16 B)
+constexpr int kBiasTileBytesT = 2048;
+constexpr int kSmemSigT = kSmemBiasTileT + kBiasTileBytesT;
 constexpr int kSmemTotalT = kSmemSigT + 128 * 4;
 static_assert(kSmemTotalT <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 constexpr int kThreadsT = 320;
 constexpr int kProducerWarpT = 8, kMmaWarpT = 9;
 
-__host__ __device__ constexpr int head_bias(int job) { return job <= 9 ? job * 256 : 9 * 256 + 128; }
 __host__ __device__ constexpr int job_layer(int j) { return j <= 9 ? j : (int)LRGB; }      // L0..L9 = 0..9
 __host__ __device__ constexpr int job_nchunks(int j) { return j == 0 ? 2 : j == 5 ? 10 : j == 9 ? 9 : j == 10 ? 4 : 8; }
 __host__ __device__ constexpr int job_nenc(int j) { return (j == 0 || j == 5) ? 2 : j == 9 ? 1 : 0; }
@@ -62,7 +64,11 @@ __host__ __device__ constexpr uint32_t job_ofs(int j) {
     for (int i = 0; i < j; ++i) o += (uint32_t)job_nchunks(i) * (uint32_t)job_rows(i) * 128u;
     return o;
 }
-constexpr uint32_t kImageBytes = job_ofs(kJobs);
+constexpr uint32_t kChunksBytes = job_ofs(kJobs);
+// behind the chunks: the bias tiles [job][cta rank][kBiasTileBytesT] -- the layer bias as a tensor-core B operand: N-row i
+// of the CTA's share is the 16 bytes [hi, mid, lo, 0] in tf32 (hi + mid + lo = the fp32 bias exactly); the first MMA of a
+// layer multiplies the "ones" A operand [1, 1, 1, 0 | 0 ...] with it (accumulate off), as in the 16-bit pair kernel
+constexpr uint32_t kImageBytes = kChunksBytes + kJobs * 2 * kBiasTileBytesT;
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t d;
@@ -84,6 +90,21 @@ __device__ __forceinline__ void chunk_k_range(int j, int i, int& k0, int& kvalid
 __global__ void pack_tf32_kernel(const float* __restrict__ P /* one model */, uint8_t* __restrict__ img) {
     const uint32_t byte = (uint32_t)(blockIdx.x * blockDim.x + threadIdx.x) * 16u;
     if (byte >= kImageBytes) return;
+    if (byte >= kChunksBytes) {          // bias tile row: (job, rank, row)
+        const uint32_t i = (byte - kChunksBytes) >> 4;
+        const int job = (int)(i >> 8), rnk = (int)((i >> 7) & 1), row = (int)(i & 127);
+        const int rows = job_rows(job) / 2, n = rnk * rows + row, l = job_layer(job);
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (row < rows && n < layer_dim(l).fan_out) {
+            const float b = P[bias_offset(l) + n];
+            v[0] = to_tf32(b);
+            const float r1 = b - __uint_as_float(v[0]);
+            v[1] = to_tf32(r1);
+            v[2] = to_tf32(r1 - __uint_as_float(v[1]));
+        }
+        *reinterpret_cast<uint4*>(img + byte) = make_uint4(v[0], v[1], v[2], v[3]);
+        return;
+    }
     int j = 0;
 #pragma unroll 1
     while (j + 1 < kJobs && byte >= job_ofs(j + 1)) ++j;
@@ -148,17 +169,17 @@ __device__ __forceinline__ void store_chunk_row(uint8_t* chunk, int row, const f
             make_uint4(to_tf32(e[4 * u]), to_tf32(e[4 * u + 1]), to_tf32(e[4 * u + 2]), to_tf32(e[4 * u + 3]));
 }
 
-// 32 accumulator columns of this thread's row -> + bias -> (ReLU) -> tf32 -> one swizzled chunk row
+// 32 accumulator columns of this thread's row (the bias is already in the accumulator) -> (ReLU) -> tf32 -> one swizzled
+// chunk row
 template <bool kRelu, bool kSigma>
-__device__ __forceinline__ void drain32(const uint32_t (&rr)[32], const float* bias, uint8_t* chunk, int row, const float* wsig, float (&sg)[4]) {
+__device__ __forceinline__ void drain32(const uint32_t (&rr)[32], uint8_t* chunk, int row, const float* wsig, float (&sg)[4]) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-        const float4 bb = reinterpret_cast<const float4*>(bias)[u];
-        float v0 = __uint_as_float(rr[4 * u + 0]) + bb.x, v1 = __uint_as_float(rr[4 * u + 1]) + bb.y;
-        float v2 = __uint_as_float(rr[4 * u + 2]) + bb.z, v3 = __uint_as_float(rr[4 * u + 3]) + bb.w;
+        float v0 = __uint_as_float(rr[4 * u + 0]), v1 = __uint_as_float(rr[4 * u + 1]);
+        float v2 = __uint_as_float(rr[4 * u + 2]), v3 = __uint_as_float(rr[4 * u + 3]);
         if (kRelu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
         if (kSigma) {      // sigma head on the fp32 activations (core/model.py:375)
-            const float4 w = reinterpret_cast<const float4*>(wsig)[u];
+            const float4 w = __ldg(reinterpret_cast<const float4*>(wsig) + u);
             sg[0] = fmaf(v0, w.x, sg[0]); sg[1] = fmaf(v1, w.y, sg[1]); sg[2] = fmaf(v2, w.z, sg[2]); sg[3] = fmaf(v3, w.w, sg[3]);
         }
         *reinterpret_cast<uint4*>(chunk + swz(row, u)) = make_uint4(to_tf32(v0), to_tf32(v1), to_tf32(v2), to_tf32(v3));
@@ -184,8 +205,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
     auto chunk_ready = [&](int c) { return sbar + 8 * (2 * kStagesT + c); };          // leader: 4 warps x 2 CTAs
     const uint32_t enc_ready = sbar + 8 * (2 * kStagesT + 8);                         // leader: 8 warps x 2 CTAs
     auto acc_full = [&](int b) { return sbar + 8 * (2 * kStagesT + 9 + b); };         // both CTAs (multicast commit)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemBarT + 8 * (2 * kStagesT + 11));
-    float* s_heads = reinterpret_cast<float*>(smem + kSmemHeadsT);
+    const uint32_t bias_full = sbar + 8 * (2 * kStagesT + 11), bias_empty = sbar + 8 * (2 * kStagesT + 12);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kSmemBarT + 8 * (2 * kStagesT + 13));
     float* s_sig = reinterpret_cast<float*>(smem + kSmemSigT);
 
     if (threadIdx.x == 0) {
@@ -193,9 +214,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
         for (int c = 0; c < 8; ++c) mbar_init(chunk_ready(c), 8);
         mbar_init(enc_ready, 16);
         mbar_init(acc_full(0), 1); mbar_init(acc_full(1), 1);
+        mbar_init(bias_full, rank == 0 ? 2 : 1);     // like ring_full: own expect_tx arrive (+ the peer's relay in the leader)
+        mbar_init(bias_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < kHeadTotal; i += kThreadsT) s_heads[i] = __ldg(p.heads + i);
+    if (threadIdx.x < 16) {
+        // "ones" A operand of the bias step: core matrix 0 = 8 rows x [1, 1, 1, 0] (tf32), core matrix 1 = zeros; its
+        // descriptor has SBO = 0, so all sixteen 8-row groups of the 128-row tile read these same 256 bytes
+        const uint32_t one = __float_as_uint(1.0f);
+        reinterpret_cast<uint4*>(smem + kSmemOnesT)[threadIdx.x] = threadIdx.x < 8 ? make_uint4(one, one, one, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
     cluster_sync_all();
     if (warp == kMmaWarpT) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
@@ -211,10 +240,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
     if (warp == kProducerWarpT) {
         // ===================== weight producer: this CTA's half of every chunk =====================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, bphase = 0;
             for (int tp = cluster_id; tp < tpairs; tp += num_clusters)
 #pragma unroll 1
                 for (int j = 0; j < kJobs; ++j) {
+                    {   // this CTA's share of the layer's bias tile (single buffer, released by the bias MMA's commit)
+                        const uint32_t bbytes = (uint32_t)job_rows(j) * 8u;
+                        mbar_wait(bias_empty, bphase ^ 1);
+                        mbar_expect_tx(bias_full, bbytes);
+                        bulk_g2s(sbase + kSmemBiasTileT, p.wimg + kChunksBytes + (uint32_t)(j * 2 + (int)rank) * kBiasTileBytesT, bbytes, bias_full);
+                        bphase ^= 1;
+                    }
                     const uint32_t half_bytes = (uint32_t)job_rows(j) * 64u;
                     const uint8_t* src = p.wimg + job_ofs(j) + rank * half_bytes;
                     const int NC = job_nchunks(j);
@@ -231,15 +267,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
         if (rank == 1) {
             // ===================== peer: relay "my half of the stage has landed" to the leader =====================
             if (lane == 0) {
-                uint32_t stage = 0, phase = 0;
+                uint32_t stage = 0, phase = 0, bphase = 0;
+                const uint32_t bias_full_leader = mapa(bias_full, 0);
                 for (int tp = cluster_id; tp < tpairs; tp += num_clusters)
 #pragma unroll 1
-                    for (int j = 0; j < kJobs; ++j)
+                    for (int j = 0; j < kJobs; ++j) {
+                        mbar_wait(bias_full, bphase);
+                        mbar_arrive_cluster(bias_full_leader);
+                        bphase ^= 1;
                         for (int i = 0; i < job_nchunks(j); ++i) {
                             mbar_wait(ring_full(stage), phase);
                             mbar_arrive_cluster(mapa(ring_full(stage), 0));
                             if (++stage == kStagesT) { stage = 0; phase ^= 1; }
                         }
+                    }
             }
         } else {
             // ===================== leader: MMA issuer for the pair =====================
@@ -247,7 +288,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
             const uint32_t ring_lo = ((sbase + kSmemRingT) >> 4) & 0x3FFFu;
             const uint32_t act_lo = ((sbase + kSmemActT) >> 4) & 0x3FFFu, enc_lo = ((sbase + kSmemEncT) >> 4) & 0x3FFFu;
             constexpr uint32_t id256 = umma_idesc_pair(2, 256), id128 = umma_idesc_pair(2, 128), id16 = umma_idesc_pair(2, 16);
-            uint32_t stage = 0, phase = 0, chunk_phase_bits = 0, enc_phase = 0;
+            uint32_t stage = 0, phase = 0, chunk_phase_bits = 0, enc_phase = 0, bphase = 0;
+            // no-swizzle K-major descriptors of the bias step: A = the ones atom (LBO 128 B between its two core matrices,
+            // SBO 0: every 8-row group aliases it), B = the bias tile (SBO 128 B between 8-row groups, LBO 0: k 4..7 alias
+            // k 0..3 and meet A's zeros)
+            const uint64_t ones_desc = (uint64_t)(((sbase + kSmemOnesT) >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | (1ull << 46);
+            const uint64_t biast_desc = (uint64_t)(((sbase + kSmemBiasTileT) >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
             for (int tp = cluster_id; tp < tpairs; tp += num_clusters) {
 #pragma unroll 1
                 for (int j = 0; j < kJobs; ++j) {
@@ -257,6 +303,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                     const uint32_t d = tmem_base + (uint32_t)(buf * 256);
                     const bool wait_enc = (j == 0 || j == 9);         // a freshly written encoding buffer
                     if (elect_one_sync()) {
+                        // the layer starts from its bias: D = ones . bias_tile^T (accumulate off). The accumulator is free:
+                        // the previous layer's MMAs, all issued, waited for every chunk of the epilogue that last read it.
+                        mbar_wait_cluster(bias_full, bphase);
+                        tc_fence_after();
+                        umma_tf32_pair(d, ones_desc, biast_desc, idesc, 0u);
+                        umma_commit_pair(bias_empty);
                         if (wait_enc) { mbar_wait_cluster(enc_ready, enc_phase); tc_fence_after(); }
                         uint32_t st = stage, ph = phase;
 #pragma unroll 1
@@ -273,7 +325,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                             const uint32_t b_lo = ring_lo + st * (kChunk >> 4);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)      // 4 x K=8 (32 bytes of a 128-byte swizzled row each)
-                                umma_tf32_pair(d, umma_desc_from_lo(a_lo + 2 * k), umma_desc_from_lo(b_lo + 2 * k), idesc, (i | k) ? 1u : 0u);
+                                umma_tf32_pair(d, umma_desc_from_lo(a_lo + 2 * k), umma_desc_from_lo(b_lo + 2 * k), idesc, 1u);
                             umma_commit_pair(ring_empty(st));
                             if (++st == kStagesT) { st = 0; ph ^= 1; }
                         }
@@ -281,6 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                     }
                     __syncwarp();
                     // every lane advances the pipeline state
+                    bphase ^= 1;
                     if (wait_enc) enc_phase ^= 1;
                     chunk_phase_bits ^= (1u << (NC - NE)) - 1u;
                     phase ^= ((stage + (uint32_t)NC) / kStagesT) & 1u;
@@ -296,7 +349,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t enc_ready_leader = mapa(enc_ready, 0);
         uint32_t acc_phase_bits = 0;
-        const float* wsig = s_heads + kHeadWsig;
+        const float* wsig = p.heads + kHeadWsig;        // fp32 sigma kernel, read through L1 (the same 1 KB for every thread)
+        const float bsig = __ldg(p.heads + kHeadBsig);
 
         auto load_row = [&](int tile, RowT& rc, float (&xyz)[3]) {
             rc.grow = (int64_t)tile * kTileRows + row;
@@ -346,7 +400,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                 acc_phase_bits ^= 1u << buf;
                 tc_fence_after();
                 const uint32_t tcols = tmem_lane + (uint32_t)(buf * 256);
-                const float* bias = s_heads + head_bias(j);
                 if (j < 10) {
                     // The two groups take the 32-column chunks ALTERNATELY (group g: chunks g, g + 2, g + 4, ...), so that
                     // chunks become ready in the order the next layer's MMAs consume them, two at a time: with each
@@ -361,9 +414,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                             const int ch = grp + 2 * c;
                             tmem_ld_wait(r[c & 1]);
                             if (c + 1 < nch) tmem_ld32(tcols + 32u * (ch + 2), r[(c + 1) & 1]);
-                            if (j == 7) drain32<true, true>(r[c & 1], bias + 32 * ch, act + ch * kChunk, row, wsig + 32 * ch, sg);
-                            else if (j == 8) drain32<false, false>(r[c & 1], bias + 32 * ch, act + ch * kChunk, row, wsig, sg);
-                            else drain32<true, false>(r[c & 1], bias + 32 * ch, act + ch * kChunk, row, wsig, sg);
+                            if (j == 7) drain32<true, true>(r[c & 1], act + ch * kChunk, row, wsig + 32 * ch, sg);
+                            else if (j == 8) drain32<false, false>(r[c & 1], act + ch * kChunk, row, wsig, sg);
+                            else drain32<true, false>(r[c & 1], act + ch * kChunk, row, wsig, sg);
                             signal(mapa(chunk_ready(ch), 0));
                         }
                     }
@@ -384,7 +437,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                         const float part = (sg[0] + sg[1]) + (sg[2] + sg[3]);
                         if (grp == 1) s_sig[row] = part;
                         named_bar_sync(1, 256);
-                        if (grp == 0 && cur.valid) p.sigma[cur.grow] = fmaxf(part + s_sig[row] + s_heads[kHeadBsig], 0.f);
+                        if (grp == 0 && cur.valid) p.sigma[cur.grow] = fmaxf(part + s_sig[row] + bsig, 0.f);
                     }
                     if (j == 9) {
                         // dense_9 has consumed enc_dir: encode the next tile now
@@ -404,7 +457,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsT, 1) mlp_tf
                         if (cur.valid) {
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
-                                const float x = __uint_as_float(r[c]) + bias[c];
+                                const float x = __uint_as_float(r[c]);        // bias included by the tensor core
                                 p.rgb[3 * cur.grow + c] = 1.f / (1.f + expf(-x));
                             }
                         }
