@@ -235,7 +235,7 @@ class NeRF:
         # vs 5.43 sequential, 32 and 64 worse - both phases slow down in proportion to the SMs they lose, so the overlap
         # buys nothing; kept as an option because the phase API is what a different schedule would build on.
         self._num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count if torch.cuda.is_available() else 148
-        self._dw_overlap_sms = int(os.environ.get("NERFB200_DW_OVERLAP_SMS", "0"))
+        self._dw_overlap_sms = 0          # (an attribute, not an environment switch: tests set it to exercise the phase API)
         self._side_stream = None
         offs = _lib.param_offsets()
         self._variables = []
