@@ -13,7 +13,6 @@ and Adam is one fused launch.
 import ctypes as C
 import functools
 import math
-import os
 
 import numpy as np
 import torch
