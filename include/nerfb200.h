@@ -161,6 +161,21 @@ NERFB200_API int nerfb200_mlp_backward_data(nerfb200_ctx* ctx, int which, int64_
 NERFB200_API int nerfb200_mlp_backward_weights(nerfb200_ctx* ctx, int which, int64_t B, int S, float* flat_grads,
                                   int precision, void* workspace, void* stash, int max_sms, void* stream);
 
+/* ---- a11: NeRF.forward (core/model.py:57-125) as ONE call --------------------------------------------
+ * stratified sampling -> coarse MLP -> integrator -> hierarchical sampling -> fine MLP -> integrator for B rays, every
+ * launch on `stream`, the intermediates (sample positions, per-sample rgb/sigma, coarse weights) in `workspace`
+ * (nerfb200_forward_workspace_bytes): nothing is allocated and nothing returns to the host in between. Tensor-core
+ * precisions only (bf16 / fp16 / tf32; pack_weights first). u_coarse / u_fine / seed / step_state / ray0 as in the
+ * samplers. Outputs per model: pred_rgb [B,3], pred_depth [B], acc_map [B], weights [B,S] (the weights may be NULL) --
+ * the four entries of the reference's result dictionaries (utils/ray_utils.py:546-551). */
+NERFB200_API int64_t nerfb200_forward_workspace_bytes(int64_t B, int Nc, int Nf);
+NERFB200_API int nerfb200_forward(nerfb200_ctx* ctx, int64_t B, int Nc, int Nf, int lin_inv_depth, int perturb, int white_bg,
+                     const float* rays_o, const float* rays_d, const float* near, const float* far,
+                     const float* u_coarse, const float* u_fine, uint64_t seed, const int64_t* step_state, int64_t ray0,
+                     const float* flat_params, int precision, void* workspace,
+                     float* coarse_rgb, float* coarse_depth, float* coarse_acc, float* coarse_weights,
+                     float* fine_rgb, float* fine_depth, float* fine_acc, float* fine_weights, void* stream);
+
 /* ---- a7-a9: volume-rendering integrator --------------------------------------------------
  * sigma_to_alpha / compute_weights / post_process_model_output (utils/ray_utils.py:408-551):
  * delta_i = t_{i+1}-t_i, delta_last = 1e10; alpha = 1-exp(-sigma*delta);

@@ -44,6 +44,9 @@ SIGNATURES = {
     "nerfb200_mlp_backward": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "nerfb200_mlp_backward_data": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "nerfb200_mlp_backward_weights": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "nerfb200_forward_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "nerfb200_forward": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _i64, _vp, _i32, _vp,
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_composite_fwd": (_i32, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_composite_bwd": (_i32, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "nerfb200_sample_fine": (_i32, [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _u64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -128,4 +128,54 @@ int nerfb200_mlp_backward_weights(nerfb200_ctx* ctx, int which, int64_t B, int S
                                (cudaStream_t)stream);
 }
 
+// ---- a11: the whole ray march of NeRF.forward (core/model.py:57-125) as ONE call -------------------------------------
+// stratified sampling -> coarse MLP -> integrator -> hierarchical sampling -> fine MLP -> integrator, every launch on
+// `stream`, intermediates in the caller's workspace (no allocation, nothing returns to the host in between).
+static inline int64_t align256(int64_t n) { return (n + 255) & ~(int64_t)255; }
+
+int64_t nerfb200_forward_workspace_bytes(int64_t B, int Nc, int Nf) {
+    if (B < 0 || Nc < 2 || Nf < 1) return -1;
+    const int64_t S = Nc + Nf;
+    // t_c [B,Nc], edges [B,Nc+1], rgb_c [B*Nc,3], sigma_c [B*Nc], weights_c [B,Nc] (when the caller does not want them),
+    // t_f [B,S], rgb_f [B*S,3], sigma_f [B*S]
+    return align256(4 * B * Nc) + align256(4 * B * (Nc + 1)) + align256(12 * B * Nc) + align256(4 * B * Nc) + align256(4 * B * Nc) +
+           align256(4 * B * S) + align256(12 * B * S) + align256(4 * B * S);
+}
+
+int nerfb200_forward(nerfb200_ctx* ctx, int64_t B, int Nc, int Nf, int lin_inv_depth, int perturb, int white_bg,
+                     const float* rays_o, const float* rays_d, const float* near, const float* far, const float* u_coarse,
+                     const float* u_fine, uint64_t seed, const int64_t* step_state, int64_t ray0, const float* flat_params,
+                     int precision, void* workspace, float* c_rgb, float* c_depth, float* c_acc, float* c_weights, float* f_rgb,
+                     float* f_depth, float* f_acc, float* f_weights, void* stream) {
+    NB_CHECK_ARG(ctx != nullptr, "forward: NULL context");
+    NB_CHECK_ARG(B >= 0 && Nc >= 2 && Nf >= 1, "forward: bad shape B=%lld Nc=%d Nf=%d", (long long)B, Nc, Nf);
+    NB_CHECK_ARG(precision >= NERFB200_FP32 && precision <= NERFB200_TF32, "forward: unknown precision %d", precision);
+    if (B == 0) return 0;
+    NB_CHECK_ARG(rays_o && rays_d && near && far && workspace && c_rgb && c_depth && c_acc && f_rgb && f_depth && f_acc,
+                 "forward: NULL tensor");
+    if (precision == NERFB200_FP32) {
+        set_error("forward: the one-call ray march exists for the tensor-core precisions (the fp32 check path needs its own MLP workspace)");
+        return NERFB200_ENOTSUP;
+    }
+    const int S = Nc + Nf;
+    uint8_t* w = (uint8_t*)workspace;
+    auto take = [&](int64_t bytes) { float* p = (float*)w; w += align256(bytes); return p; };
+    float* t_c = take(4 * B * Nc);
+    float* edges = take(4 * B * (Nc + 1));
+    float* rgb_c = take(12 * B * Nc);
+    float* sig_c = take(4 * B * Nc);
+    float* w_c = take(4 * B * Nc);
+    float* t_f = take(4 * B * S);
+    float* rgb_f = take(12 * B * S);
+    float* sig_f = take(4 * B * S);
+    if (c_weights) w_c = c_weights;
+    int rc;
+    if ((rc = nerfb200_sample_coarse(B, Nc, lin_inv_depth, perturb, near, far, u_coarse, seed, step_state, ray0, t_c, edges, stream))) return rc;
+    if ((rc = nerfb200_mlp_forward(ctx, NERFB200_COARSE, B, Nc, rays_o, rays_d, t_c, flat_params, rgb_c, sig_c, precision, nullptr, nullptr, stream))) return rc;
+    if ((rc = nerfb200_composite_fwd(B, Nc, sig_c, rgb_c, t_c, white_bg, w_c, c_rgb, c_depth, c_acc, stream))) return rc;
+    if ((rc = nerfb200_sample_fine(B, Nc, Nf, w_c, edges, t_c, u_fine, seed, step_state, ray0, t_f, nullptr, nullptr, nullptr, stream))) return rc;
+    if ((rc = nerfb200_mlp_forward(ctx, NERFB200_FINE, B, S, rays_o, rays_d, t_f, flat_params, rgb_f, sig_f, precision, nullptr, nullptr, stream))) return rc;
+    return nerfb200_composite_fwd(B, S, sig_f, rgb_f, t_f, white_bg, f_weights, f_rgb, f_depth, f_acc, stream);
+}
+
 }  // extern "C"

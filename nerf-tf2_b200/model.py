@@ -259,6 +259,7 @@ class NeRF:
         self.world_size, self.rank = 1, 0
         self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
         self.graph_overlap_allreduce = True   # the same fork/join inside a captured step
+        self.fused_forward = True         # forward()/predict()/render: the whole march as one C-ABI call (nerfb200_forward)
         self.use_cuda_graph = bool(int(cuda_graph))     # train_step as one CUDA graph per batch shape (after two eager steps)
         self._graphs, self._step_dev, self._step_dev_host = {}, None, None
         self._step_counter = 0
@@ -368,6 +369,10 @@ class NeRF:
         # the sampling noise is keyed by (rng_seed, step, global ray id); with a device-resident step state the step is
         # XORed in on the device, so that a captured step draws fresh noise at every replay
         seed = (self.rng_seed << 20) ^ (self._step_counter if _step_state is None else 0)
+        if _train is None and self.fused_forward and precision != FP32:
+            # the whole march as ONE C-ABI call (nerfb200_forward): six to eight launches back to back, intermediates in a
+            # persistent workspace. (With need_weights=False the coarse weights stay in the workspace too.)
+            return self._forward_one_call(rays_o, rays_d, near, far, u_coarse, u_fine, seed, _step_state, ray0, precision, need_weights)
         t_c, edges = ray_utils.sample_coarse(s.N_coarse, s.lin_inv_depth, s.perturb, near, far, u_coarse, seed, ray0,
                                              step_state=_step_state)
         st_c = st_f = None
@@ -383,6 +388,30 @@ class NeRF:
         if _train is not None:
             _train.update(dict(t_c=t_c, t_f=t_f, rgb_c=rgb_c, sig_c=sig_c, rgb_f=rgb_f, sig_f=sig_f,
                                st_c=st_c, st_f=st_f))
+        return pp_c, pp_f
+
+    def _forward_one_call(self, rays_o, rays_d, near, far, u_coarse, u_fine, seed, step_state, ray0, precision, need_weights):
+        s = self.params.sampling
+        lib = load()
+        B, Nc, Nf = int(rays_o.shape[0]), int(s.N_coarse), int(s.N_fine)
+        f32 = dict(device=self.device, dtype=torch.float32)
+        pp_c = {"acc_map": torch.empty((B,), **f32), "pred_rgb": torch.empty((B, 3), **f32), "pred_depth": torch.empty((B,), **f32)}
+        pp_f = {"acc_map": torch.empty((B,), **f32), "pred_rgb": torch.empty((B, 3), **f32), "pred_depth": torch.empty((B,), **f32)}
+        if need_weights:
+            pp_c["weights"] = torch.empty((B, Nc), **f32)
+            pp_f["weights"] = torch.empty((B, Nc + Nf), **f32)
+        if B == 0:
+            return pp_c, pp_f
+        self._sync_packed(precision)
+        ws = self._scratch("fwd_ws", lib.nerfb200_forward_workspace_bytes(B, Nc, Nf))
+        opt = lambda t: ptr(t.contiguous(), allow_none=True) if t is not None else C.c_void_p(0)
+        check(lib.nerfb200_forward(self._ctx, B, Nc, Nf, int(bool(s.lin_inv_depth)), int(bool(s.perturb)), int(bool(self.white_bg)),
+                                   ptr(rays_o), ptr(rays_d), ptr(near.reshape(-1).contiguous()), ptr(far.reshape(-1).contiguous()),
+                                   opt(u_coarse), opt(u_fine), seed, ptr(step_state, torch.int64, allow_none=True), ray0,
+                                   ptr(self.flat_params), precision, ptr(ws, torch.uint8),
+                                   ptr(pp_c["pred_rgb"]), ptr(pp_c["pred_depth"]), ptr(pp_c["acc_map"]), opt(pp_c.get("weights")),
+                                   ptr(pp_f["pred_rgb"]), ptr(pp_f["pred_depth"]), ptr(pp_f["acc_map"]), opt(pp_f.get("weights")),
+                                   stream_ptr()), "forward")
         return pp_c, pp_f
 
     def call(self, inputs):

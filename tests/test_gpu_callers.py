@@ -219,3 +219,30 @@ def test_render_spherical_path_script_loop(tmp_path):
     K = nb.CustomDataset.camera_model_params_to_intrinsics("SIMPLE_PINHOLE", [16.0, 6.0, 5.0])
     r = nb.render.render_view(nerf, 10, 12, pose3, b3, K, scale_factor=0.2125, c2w_W2=pose2)
     assert np.array_equal(host(r["img_u8"]).reshape(10, 12, 3), frames[1]["img_u8"])
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_one_call_forward_equals_step_by_step(precision):
+    """nerfb200_forward (the whole march of NeRF.forward, core/model.py:57-125, as one C-ABI call) returns bit for bit
+    what the same launches issued one by one from Python return: fixed uniforms and in-kernel Philox, with and without
+    the per-sample weights."""
+    import numpy as np
+    from oracle import scene as osc
+    v = osc.synthetic_view(37, 29, view=3)
+    n = 37 * 29
+    dv = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ro, rd, near, far = (dv(v[k]) for k in ("rays_o", "rays_d", "near", "far"))
+    uf = torch.rand((n, 128), device="cuda")
+    nerf = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision=precision, seed=5, rng_seed=11)
+    for kw in (dict(u_fine=uf), dict(), dict(need_weights=False), dict(ray0=12345)):
+        nerf.fused_forward = True
+        c1, f1 = nerf.forward(ro, rd, near, far, **kw)
+        nerf.fused_forward = False
+        c0, f0 = nerf.forward(ro, rd, near, far, **kw)
+        for a, b in ((c1, c0), (f1, f0)):
+            keys = [k for k in b if k in a]
+            assert set(keys) >= {"pred_rgb", "pred_depth", "acc_map"} and ("weights" in a) == (kw.get("need_weights", True))
+            for k in keys:
+                assert torch.equal(a[k], b[k]), (precision, kw.keys(), k)
+    lib = nb._lib.load()
+    assert lib.nerfb200_forward_workspace_bytes(0, 64, 128) == 0 and lib.nerfb200_forward_workspace_bytes(-1, 64, 128) == -1
