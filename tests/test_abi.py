@@ -53,6 +53,13 @@ def test_argument_validation_needs_no_gpu():
     assert lib.nerfb200_mlp_backward_data(None, 0, 1, 1, None, None, None, 1, None, None, 0, None) == 10001
     assert lib.nerfb200_mlp_backward_weights(None, 0, 1, 1, None, 1, None, None, 0, None) == 10001
     assert b"context" in lib.nerfb200_last_error()
+    # the one-call ray march validates its context, shapes and precision before touching the device
+    fwd = lambda ctx, B, prec: lib.nerfb200_forward(ctx, B, 64, 128, 1, 1, 1, None, None, None, None, None, None, 0, None, 0, None, prec,
+                                                    None, None, None, None, None, None, None, None, None, None)
+    assert fwd(None, 4, 1) == 10001 and b"context" in lib.nerfb200_last_error()
+    assert lib.nerfb200_forward_workspace_bytes(1000, 64, 128) >= 4 * 1000 * (64 + 65 + 4 * 64 + 64 + 192 + 4 * 192)
+    assert lib.nerfb200_set_option(None, 1, 1) == 10001
+    assert lib.nerfb200_step_advance(None, None) == 10001
     assert lib.nerfb200_mlp_workspace_bytes(1000, 1, 0) == 0
     assert lib.nerfb200_mlp_stash_bytes(10, 0) == 10 * (63 + 27 + 8 * 256 + 256 + 128 + 3 + 1) * 4
 

@@ -180,3 +180,36 @@ def test_train_step_cfg3_4096_rays_vs_oracle(precision):
     # PSNRMetric of the step (fine prediction) against the oracle's
     mref = rm.PSNRMetric(); mref.update_state(gt, info["pred_rgb_f"])
     assert abs(float(logs["psnr_metric"]) - float(mref.result())) <= 2e-2
+
+
+@pytest.mark.parametrize("cfg", [dict(Nc=128, Nf=256, lin=True, white=True, perturb=True),      # BASELINE cfg5's sample counts
+                                 dict(Nc=32, Nf=64, lin=False, white=False, perturb=True),      # generic sampler / integrator paths
+                                 dict(Nc=64, Nf=128, lin=False, white=False, perturb=False)])
+def test_forward_other_configurations_vs_oracle(cfg):
+    """The whole march at other settings of params.sampling / system.white_bg than the default render: 128+256 samples
+    (cfg5), linear-in-depth spacing, black background, stratified perturbation with explicit uniforms -- fp32 MLP near-exact,
+    bf16 within the stated tolerance, through the one-call entry point and step by step."""
+    H, W = 20, 15
+    n = H * W
+    v = osc.synthetic_view(H, W, view=5)
+    rng = np.random.default_rng(cfg["Nc"])
+    uc = rng.random((n, cfg["Nc"]), dtype=F32) if cfg["perturb"] else None
+    uf = rng.random((n, cfg["Nf"]), dtype=F32)
+    w = om.init_weights(9)
+    pc, pf = om.forward(w, v["rays_o"], v["rays_d"], v["near"], v["far"], cfg["Nc"], cfg["Nf"], lin_inv_depth=cfg["lin"],
+                        perturb=cfg["perturb"], white_bg=cfg["white"], u_coarse=uc, u_fine=uf)
+    p = nb.make_params({"system": {"white_bg": cfg["white"]}}, N_coarse=cfg["Nc"], N_fine=cfg["Nf"], lin_inv_depth=cfg["lin"],
+                       perturb=cfg["perturb"])
+    args = (dev(v["rays_o"]), dev(v["rays_d"]), dev(v["near"]), dev(v["far"]))
+    kw = dict(u_coarse=None if uc is None else dev(uc), u_fine=dev(uf))
+    npd = lambda d: {k: host(x) for k, x in d.items()}
+    f32 = nb.setup_model(p, precision="fp32"); f32.set_weights_from_dict(w)
+    oc, of = f32.forward(*args, **kw)
+    assert of["weights"].shape == (n, cfg["Nc"] + cfg["Nf"])
+    for k, lim in (("pred_rgb", 5e-4), ("pred_depth", 1e-3), ("acc_map", 1e-3)):
+        assert np.abs(host(oc[k]) - pc[k]).max() <= lim and np.abs(host(of[k]) - pf[k]).max() <= lim, (cfg, k)
+    b16 = nb.setup_model(p, precision="bf16"); b16.set_weights_from_dict(w)
+    for fused in (True, False):
+        b16.fused_forward = fused
+        oc, of = b16.forward(*args, **kw)
+        check_render("bf16", npd(oc), npd(of), pc, pf)
