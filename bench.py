@@ -585,11 +585,12 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
     batch = ((ro, rd, near, far), (rgb,))
     steps = 50
 
-    def run(graph):
+    def run(graph, peer=True):
         tn = nb.setup_model(p, precision=tp if tp != "fp32" else "bf16", train_precision=tp, seed=0, cuda_graph=graph,
                             precise_last=False)
         if world > 1:
-            tn.set_distributed()
+            tn.set_distributed(peer_exchange=peer)
+        used_peer = tn._peer is not None
         for _ in range(5):
             tn.train_step(batch)
         barrier()
@@ -604,18 +605,27 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
             ms = nb.dist.max_over_ranks(ms, dev)
         captured = any("graph" in st for st in tn._graphs.values())
         tn.release_cuda_graphs()      # captured NCCL work must be gone before the process group is torn down
+        tn.close_distributed()        # unmaps the peers' gradient buffers (collective)
         del tn
-        return ms, captured
+        return ms, captured, used_peer
 
-    ms_eager, _ = run(False)
-    ms_graph, captured = run(True) if not args.no_train_graph else (ms_eager, False)
+    ms_eager, _, used_peer = run(False)
+    ms_graph, captured, _ = run(True) if not args.no_train_graph else (ms_eager, False, used_peer)
     ms = min(ms_eager, ms_graph) if captured else ms_eager      # `value`: the faster of the two launch modes
     sps = steps / (ms / 1e3)
+    nccl = None
+    if world > 1 and used_peer:   # the same step with the gradient handed to NCCL instead (what the peer kernel replaces)
+        ms_n, cap_n, _ = run(not args.no_train_graph, peer=False)
+        nccl = {"value": steps / (ms_n / 1e3), "ms_per_step": ms_n / steps, "cuda_graph": bool(cap_n)}
     flop = 3489024 * B * ROWS_PER_RAY
     pk = peaks()
     return {"metric": "train steps/s (4096-ray batch, coarse+fine fwd/bwd + Adam, data-parallel all-reduce)",
             "value": sps, "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "precision": tp,
             "global_batch": B, "rays_per_gpu": Bl, "achieved_tflops": flop * sps / 1e12,
+            "gradient_exchange": (None if world == 1 else
+                                  "one kernel per rank over NVLink peer memory (reduce-scatter + all-gather by loads/stores, "
+                                  "fused with Adam; csrc/peer.cu)" if used_peer else "NCCL all-reduce"),
+            "with_nccl_allreduce_instead": nccl,
             "frac_of_sustained_peak": flop * sps / 1e12 / (pk["tensor"] * world),
             "launch_mode": ("one CUDA graph per step (sampling, forwards, loss, backwards, all-reduce, Adam, repack)"
                             if captured and ms_graph <= ms_eager else "eager launches"),

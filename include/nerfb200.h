@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NERFB200_ABI_VERSION 2
+#define NERFB200_ABI_VERSION 3
 
 #define NERFB200_EINVAL   10001   /* bad argument                      */
 #define NERFB200_ENOTSUP  10002   /* shape outside the supported range */
@@ -56,6 +56,7 @@ extern "C" {
 #define NERFB200_PARAMS_TOTAL (2 * NERFB200_PARAMS_PER_MODEL)  /* coarse then fine */
 
 typedef struct nerfb200_ctx nerfb200_ctx;
+typedef struct nerfb200_peer nerfb200_peer;   /* data-parallel gradient exchange over peer memory (below) */
 
 NERFB200_API const char* nerfb200_last_error(void);
 NERFB200_API int nerfb200_abi_version(void);
@@ -220,6 +221,36 @@ NERFB200_API int nerfb200_mse_loss_grad(int64_t B, int64_t B_global, const float
 NERFB200_API int nerfb200_adam_step(int64_t n, float* params, const float* grads, float* m, float* v,
                        int64_t iterations, const int64_t* step_state /* overrides `iterations` when non-NULL */, void* stream);
 NERFB200_API int nerfb200_step_advance(int64_t* step_state /* device int64[2] */, void* stream);
+
+/* ---- (e) data-parallel training: the gradient exchange over NVLink peer memory ------------------
+ * The reference applies the gradients of ONE device's tape (core/model.py:148-171); data parallel, the flat
+ * buffer [coarse gradient | fine gradient | loss,0,0,0] has to be summed over the ranks before the replicated
+ * Adam. One process per GPU of one NVSwitch box (world <= 8):
+ *   peer_create   allocates this rank's block (a small flag header + n_floats floats, zeroed) on the current device;
+ *   peer_buffer   the n_floats floats -- the caller accumulates its local gradient there;
+ *   peer_handle   64 opaque bytes (a CUDA IPC handle) to be exchanged between the ranks by any means
+ *                 (torch.distributed.all_gather here);
+ *   peer_connect  maps every other rank's block (`handles` = world x 64 bytes, in rank order);
+ *   peer_allreduce  ONE kernel: flag barrier, every rank sums its 1/world slice of all ranks' buffers over
+ *                 NVLink in rank order and stores the sum into that slice of EVERY rank's buffer, flag barrier.
+ *                 The launch completes when the local buffer holds the full sum; all ranks receive bit-identical
+ *                 sums. Every rank must launch it the same number of times (like a collective). A rank whose peers
+ *                 do not arrive within the timeout (default 120 s) traps instead of hanging;
+ *   peer_allreduce_adam  the same exchange followed, in the same launch, by nerfb200_adam_step over the first n
+ *                 floats of the summed buffer (params/m/v: local, 16-byte aligned, n a multiple of 4): identical
+ *                 arithmetic to peer_allreduce + adam_step.
+ * Flags carry an epoch kept in device memory, so both launches can be captured in a CUDA graph and replayed. */
+NERFB200_API int nerfb200_peer_create(int world, int rank, int64_t n_floats, nerfb200_peer** peer);
+NERFB200_API int nerfb200_peer_buffer(nerfb200_peer* peer, float** buffer);
+NERFB200_API int nerfb200_peer_handle(nerfb200_peer* peer, unsigned char* handle64);
+NERFB200_API int nerfb200_peer_connect(nerfb200_peer* peer, const unsigned char* handles);
+NERFB200_API int nerfb200_peer_set_timeout(nerfb200_peer* peer, int seconds);
+NERFB200_API int nerfb200_peer_allreduce(nerfb200_peer* peer, void* stream);
+NERFB200_API int nerfb200_peer_allreduce_adam(nerfb200_peer* peer, int64_t n, float* params, float* m, float* v,
+                                 int64_t iterations, const int64_t* step_state, void* stream);
+NERFB200_API int nerfb200_peer_status(nerfb200_peer* peer, int* status /* 0, or the barrier (1/2) a wait timed out at */);
+NERFB200_API int nerfb200_peer_disconnect(nerfb200_peer* peer);   /* unmaps the other ranks' blocks */
+NERFB200_API int nerfb200_peer_destroy(nerfb200_peer* peer);      /* + frees this rank's block: only after EVERY rank has disconnected */
 
 /* ---- a15: depth map type_2 (utils/ray_utils.py:122-130) -------------------------------------
  * z of the point o + d*depth/scale in the camera frame. */

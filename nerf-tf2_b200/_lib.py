@@ -53,6 +53,16 @@ SIGNATURES = {
     "nerfb200_mse_loss_grad": (_i32, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_adam_step": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nerfb200_step_advance": (_i32, [_vp, _vp]),
+    "nerfb200_peer_create": (_i32, [_i32, _i32, _i64, C.POINTER(_vp)]),
+    "nerfb200_peer_buffer": (_i32, [_vp, C.POINTER(_vp)]),
+    "nerfb200_peer_handle": (_i32, [_vp, C.c_char_p]),
+    "nerfb200_peer_connect": (_i32, [_vp, C.c_char_p]),
+    "nerfb200_peer_set_timeout": (_i32, [_vp, _i32]),
+    "nerfb200_peer_allreduce": (_i32, [_vp, _vp]),
+    "nerfb200_peer_allreduce_adam": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nerfb200_peer_status": (_i32, [_vp, C.POINTER(_i32)]),
+    "nerfb200_peer_disconnect": (_i32, [_vp]),
+    "nerfb200_peer_destroy": (_i32, [_vp]),
     "nerfb200_depth_type2": (_i32, [_i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _dbl, _vp, _vp, _vp]),
     "nerfb200_sample_pixels": (_i32, [_i64, _i64, _u64, _u64, _vp, _vp]),
     "nerfb200_gather_rgb_u8": (_i32, [_i64, _vp, _vp, _vp, _vp]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnerfb200.so")
-SOURCES = ["rays.cu", "composite.cu", "sampler.cu", "optim.cu", "mlp_ref.cu", "mlp_tc.cu", "mlp_tc_tf32.cu", "mlp_tc_train.cu", "mlp_api.cu"]
+SOURCES = ["rays.cu", "composite.cu", "sampler.cu", "optim.cu", "peer.cu", "mlp_ref.cu", "mlp_tc.cu", "mlp_tc_tf32.cu", "mlp_tc_train.cu", "mlp_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static"]
 

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#include <math.h>
 #include <atomic>
 
 #include "../../include/nerfb200.h"
@@ -143,6 +145,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keras OptimizerV2 Adam._resource_apply_dense (non-amsgrad; core/model.py:413-418), shared by
+// adam_kernel (optim.cu) and the fused exchange + Adam kernel (peer.cu).
+// lr_t = lr(iterations) * sqrt(1 - b2^t) / (1 - b1^t), t = iterations + 1; lr = ExponentialDecay(5e-4, 500000, 0.1), staircase=False
+__host__ __device__ inline float adam_lr_t(int64_t iterations) {
+    const double beta1 = 0.9, beta2 = 0.999;
+    const double t = (double)(iterations + 1);
+    const float lr = (float)(5e-4 * pow(0.1, (double)iterations / 500000.0));
+    return lr * (float)sqrt(1.0 - pow(beta2, t)) / (float)(1.0 - pow(beta1, t));
+}
+// m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr_t m / (sqrt(v) + eps): separate IEEE operations, no contraction
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float lr_t) {
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f;
+    m = __fadd_rn(__fmul_rn(m, b1), __fmul_rn(g, 1.f - b1));
+    v = __fadd_rn(__fmul_rn(v, b2), __fmul_rn(__fmul_rn(g, g), 1.f - b2));
+    p = __fsub_rn(p, __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
 }
 
 }  // namespace nb

@@ -32,17 +32,8 @@ __global__ void mse_loss_grad_kernel(int64_t B, float inv_n, const float* __rest
     }
 }
 
-// Keras OptimizerV2 Adam._resource_apply_dense (non-amsgrad): SURVEY.md Appendix A.
-// lr_t = lr(iterations) * sqrt(1 - b2^t) / (1 - b1^t), t = iterations + 1; lr = ExponentialDecay(5e-4, 500000, 0.1), staircase=False
-__host__ __device__ inline float adam_lr_t(int64_t iterations) {
-    const double beta1 = 0.9, beta2 = 0.999;
-    const double t = (double)(iterations + 1);
-    const float lr = (float)(5e-4 * pow(0.1, (double)iterations / 500000.0));
-    return lr * (float)sqrt(1.0 - pow(beta2, t)) / (float)(1.0 - pow(beta1, t));
-}
-
 __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, float lr_t, const int64_t* __restrict__ step_dev, float b1, float b2, float eps) {
+                            float* __restrict__ v, float lr_t, const int64_t* __restrict__ step_dev) {
     if (step_dev) {          // device-resident iteration counter (CUDA-graph replays): same formula, evaluated once per block
         __shared__ float s_lr_t;
         if (threadIdx.x == 0) s_lr_t = adam_lr_t(step_dev[0]);
@@ -51,12 +42,11 @@ __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __res
     }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float gi = g[i];
-    float mi = __fadd_rn(__fmul_rn(m[i], b1), __fmul_rn(gi, 1.f - b1));
-    float vi = __fadd_rn(__fmul_rn(v[i], b2), __fmul_rn(__fmul_rn(gi, gi), 1.f - b2));
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, g[i], lr_t);
     m[i] = mi;
     v[i] = vi;
-    p[i] = __fsub_rn(p[i], __fdiv_rn(__fmul_rn(lr_t, mi), __fadd_rn(__fsqrt_rn(vi), eps)));
+    p[i] = pi;
 }
 
 __global__ void step_advance_kernel(int64_t* __restrict__ step) { step[0] += 1; step[1] += 1; }
@@ -83,8 +73,7 @@ int nerfb200_adam_step(int64_t n, float* params, const float* grads, float* m, f
     NB_CHECK_ARG(n >= 0 && params && grads && m && v && iterations >= 0, "adam_step: bad arguments");
     if (n == 0) return 0;
     const float lr_t = adam_lr_t(iterations);
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, params, grads, m, v, lr_t, step_state, 0.9f,
-                                                                             0.999f, 1e-7f);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, params, grads, m, v, lr_t, step_state);
     NB_LAUNCH_CHECK();
     return 0;
 }

@@ -182,6 +182,25 @@ class _Adam:
             self.iterations += 1
         self._nerf._dirty = True
 
+    def exchange_and_apply(self, peer, step_state=None):
+        """Data parallel: the gradient exchange over peer memory and the Adam step as ONE launch
+        (nerfb200_peer_allreduce_adam) -- same arithmetic as an all-reduce followed by apply_gradients."""
+        n = self._nerf.flat_params.numel()
+        with torch.cuda.device(self._nerf.device):
+            check(load().nerfb200_peer_allreduce_adam(peer, n, ptr(self._nerf.flat_params), ptr(self.m), ptr(self.v),
+                                                      self.iterations, ptr(step_state, torch.int64, allow_none=True),
+                                                      stream_ptr()), "peer_allreduce_adam")
+        if step_state is None:
+            self.iterations += 1
+        self._nerf._dirty = True
+
+
+class _DeviceFloats:
+    """Exposes `n` floats of device memory owned by the C library to torch (CUDA array interface)."""
+
+    def __init__(self, address, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(address), False), "version": 2}
+
 
 class History:
     def __init__(self):
@@ -257,6 +276,9 @@ class NeRF:
         self.metrics = []
         self.process_group = None
         self.world_size, self.rank = 1, 0
+        self._peer_owner = None
+        self._peer = None                 # nerfb200_peer handle: the gradient exchange over NVLink peer memory
+        self.fuse_exchange_adam = True    # ... with the Adam step in the same launch
         self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
         self.graph_overlap_allreduce = True   # the same fork/join inside a captured step
         self.fused_forward = True         # forward()/predict()/render: the whole march as one C-ABI call (nerfb200_forward)
@@ -270,6 +292,7 @@ class NeRF:
             if getattr(self, "_ctx", None):
                 load().nerfb200_destroy(self._ctx)
                 self._ctx = None
+            # a peer block is NOT freed here: other ranks may still have it mapped (close_distributed does it in step)
         except Exception:
             pass
 
@@ -284,13 +307,86 @@ class NeRF:
         self.optimizer = _Adam(self)
         self.metrics = list(metrics) if metrics is not None else [ops.PSNRMetric()]
 
-    def set_distributed(self, process_group=None):
-        """Data-parallel training over torch.distributed (NCCL on GPUs): the 4096-ray batch is split
-        across ranks and the flat gradient is all-reduced once per step."""
+    def set_distributed(self, process_group=None, peer_exchange=True):
+        """Data-parallel training over torch.distributed (NCCL on GPUs): the 4096-ray batch is split across ranks and
+        the flat [gradient | loss] buffer is summed over the ranks once per step. `peer_exchange`
+        (default): the ranks map each other's gradient buffer over NVLink (CUDA IPC) and one kernel of this library
+        does the exchange -- fused with the Adam step -- instead of an NCCL all-reduce (csrc/peer.cu); NCCL then only
+        carries the 64-byte handles. Falls back to the NCCL all-reduce, with a warning, if the ranks cannot map each
+        other's memory (more than 8 ranks, several nodes, no peer access)."""
         import torch.distributed as dist
         self.process_group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.process_group)
         self.rank = dist.get_rank(self.process_group)
+        if peer_exchange and self.world_size > 1 and self._peer is None:
+            self._setup_peer_exchange()
+
+    @_on_device
+    def _setup_peer_exchange(self):
+        import torch.distributed as dist
+        import warnings
+        lib, W, n = load(), self.world_size, PARAMS_TOTAL + 4
+        h, why = C.c_void_p(), ""
+        handle = C.create_string_buffer(64)
+        ok = W <= 8
+        if not ok:
+            why = "more than 8 ranks"
+        if ok and lib.nerfb200_peer_create(W, self.rank, n, C.byref(h)) != 0:
+            ok, why = False, lib.nerfb200_last_error().decode("utf-8", "replace")
+        if ok and lib.nerfb200_peer_handle(h, handle) != 0:
+            ok, why = False, lib.nerfb200_last_error().decode("utf-8", "replace")
+        # the 64-byte handles (+ one "so far so good" byte) go round by NCCL; every rank must take the same decision
+        mine = torch.tensor(list(handle.raw) + [int(ok)], dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(W)]
+        dist.all_gather(gathered, mine, group=self.process_group)
+        blob = torch.stack(gathered).cpu().numpy()
+        buf = None
+        if ok and bool(blob[:, 64].all()):
+            if lib.nerfb200_peer_connect(h, blob[:, :64].tobytes()) != 0:
+                ok, why = False, lib.nerfb200_last_error().decode("utf-8", "replace")
+            else:
+                try:
+                    addr = C.c_void_p()
+                    check(lib.nerfb200_peer_buffer(h, C.byref(addr)), "peer_buffer")
+                    buf = torch.as_tensor(_DeviceFloats(addr.value, n), device=self.device)
+                    assert buf.data_ptr() == addr.value and buf.dtype == torch.float32 and buf.numel() == n
+                except Exception as ex:          # torch could not wrap the library's memory
+                    ok, why, buf = False, f"{type(ex).__name__}: {ex}", None
+        else:
+            ok = False
+        agreed = torch.tensor([int(ok)], dtype=torch.int32, device=self.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.process_group)
+        if not int(agreed.item()):
+            # (the block, if any, is left allocated: a peer may have mapped it already)
+            warnings.warn("peer-memory gradient exchange unavailable on some rank"
+                          + (f" (this rank: {why})" if why else "") + "; using the NCCL all-reduce")
+            return
+        buf.copy_(self._grad_buf)
+        self._peer, self._peer_owner = h, buf
+        self._grad_buf = buf
+        self.flat_grads = self._grad_buf[:PARAMS_TOTAL]
+        self._graphs.clear()              # captured steps hold the old gradient buffer
+
+    def close_distributed(self):
+        """Releases the peer mappings (collective: every rank calls it; nothing is freed while a peer may still use it)."""
+        if self._peer is None:
+            return
+        import torch.distributed as dist
+        self.release_cuda_graphs()
+        dist.barrier(group=self.process_group)
+        with torch.cuda.device(self.device):
+            old = self._grad_buf
+            if self.last_loss is not None:
+                self.last_loss = self.last_loss.clone()
+            self._grad_buf = old.clone()
+            self.flat_grads = self._grad_buf[:PARAMS_TOTAL]
+            torch.cuda.synchronize(self.device)
+            del old
+            self._peer_owner = None
+            check(load().nerfb200_peer_disconnect(self._peer), "peer_disconnect")
+            dist.barrier(group=self.process_group)
+            check(load().nerfb200_peer_destroy(self._peer), "peer_destroy")
+        self._peer = None
 
     def set_flat_params(self, flat):
         self.flat_params.copy_(torch.as_tensor(flat, dtype=torch.float32).to(self.device))
@@ -506,7 +602,7 @@ class NeRF:
                 return {m.name: m.result_async() for m in self.metrics}
         pending = []
         coarse_done = None
-        if self.world_size > 1 and self.overlap_allreduce:
+        if self.world_size > 1 and self.overlap_allreduce and self._peer is None:
             import torch.distributed as dist
 
             def coarse_done():
@@ -514,18 +610,28 @@ class NeRF:
                 # NCCL's stream next to the fine backward (it takes SMs as the persistent kernels' CTAs retire)
                 pending.append(dist.all_reduce(self._grad_buf[:PARAMS_PER_MODEL], group=self.process_group, async_op=True))
         loss, _, _ = self._loss_and_grads(ro, rd, near, far, rgb, u_coarse, u_fine, ray0, coarse_done=coarse_done)
-        if self.world_size > 1:
-            import torch.distributed as dist
-            if pending:       # fine half + [loss] tail; then both must have landed before Adam reads them
-                pending.append(dist.all_reduce(self._grad_buf[PARAMS_PER_MODEL:], group=self.process_group, async_op=True))
-                for h in pending:
-                    h.wait()
-            else:
-                dist.all_reduce(self._grad_buf, group=self.process_group)     # ONE collective: gradient + loss
-        self.optimizer.apply_gradients(self.flat_grads)
+        self._exchange_and_apply(pending)
         self._step_counter += 1
         self.last_loss = loss
         return {m.name: m.result_async() for m in self.metrics}     # no device sync: see PSNRMetric.result_async
+
+    def _exchange_and_apply(self, pending, step_state=None):
+        """Sum of the flat [gradient | loss] buffer over the ranks, then Adam (core/model.py:170-171)."""
+        if self.world_size > 1:
+            if self._peer is not None:
+                if self.fuse_exchange_adam:       # ONE launch: exchange over NVLink peer memory + Adam
+                    self.optimizer.exchange_and_apply(self._peer, step_state=step_state)
+                    return
+                check(load().nerfb200_peer_allreduce(self._peer, stream_ptr()), "peer_allreduce")
+            else:
+                import torch.distributed as dist
+                if pending:       # fine half + [loss] tail; then both must have landed before Adam reads them
+                    pending.append(dist.all_reduce(self._grad_buf[PARAMS_PER_MODEL:], group=self.process_group, async_op=True))
+                    for h in pending:
+                        h.wait()
+                else:
+                    dist.all_reduce(self._grad_buf, group=self.process_group)     # ONE collective: gradient + loss
+        self.optimizer.apply_gradients(self.flat_grads, step_state=step_state)
 
     @_on_device
     def _train_step_graphed(self, ro, rd, near, far, rgb, ray0):
@@ -559,21 +665,13 @@ class NeRF:
             try:
                 with torch.cuda.graph(g):
                     pending, coarse_done = [], None
-                    if self.world_size > 1 and self.overlap_allreduce and self.graph_overlap_allreduce:
+                    if self.world_size > 1 and self.overlap_allreduce and self.graph_overlap_allreduce and self._peer is None:
                         import torch.distributed as dist
 
                         def coarse_done():      # a fork inside the capture: NCCL's stream joins again at the wait() below
                             pending.append(dist.all_reduce(self._grad_buf[:PARAMS_PER_MODEL], group=self.process_group, async_op=True))
                     self._loss_and_grads(*static, ray0=ray0, step_state=self._step_dev, coarse_done=coarse_done)
-                    if self.world_size > 1:
-                        import torch.distributed as dist
-                        if pending:
-                            pending.append(dist.all_reduce(self._grad_buf[PARAMS_PER_MODEL:], group=self.process_group, async_op=True))
-                            for h in pending:
-                                h.wait()
-                        else:
-                            dist.all_reduce(self._grad_buf, group=self.process_group)     # ONE collective: gradient + loss
-                    self.optimizer.apply_gradients(self.flat_grads, step_state=self._step_dev)
+                    self._exchange_and_apply(pending, step_state=self._step_dev)
                     check(lib.nerfb200_step_advance(ptr(self._step_dev, torch.int64), stream_ptr()), "step_advance")
                     check(lib.nerfb200_pack_weights(self._ctx, ptr(self.flat_params), stream_ptr()), "pack_weights")
             except Exception as ex:       # e.g. a collective that cannot be captured: stay eager, loudly

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_param_layout():
     lib = _lib.load()
-    assert lib.nerfb200_abi_version() == 2
+    assert lib.nerfb200_abi_version() == 3
     offs = _lib.param_offsets()
     assert offs[0] == 0 and offs[1] == 63 * 256 and offs[-1] == _lib.PARAMS_PER_MODEL == 595844
     from oracle import model as om
@@ -61,6 +61,15 @@ def test_argument_validation_needs_no_gpu():
     assert lib.nerfb200_set_option(None, 1, 1) == 10001
     assert lib.nerfb200_step_advance(None, None) == 10001
     assert lib.nerfb200_mlp_workspace_bytes(1000, 1, 0) == 0
+    # the peer-memory gradient exchange validates world / rank / size before it allocates anything
+    h = ctypes.c_void_p()
+    assert lib.nerfb200_peer_create(9, 0, 1024, ctypes.byref(h)) == 10001 and b"world" in lib.nerfb200_last_error()
+    assert lib.nerfb200_peer_create(2, 2, 1024, ctypes.byref(h)) == 10001
+    assert lib.nerfb200_peer_create(2, 0, 1023, ctypes.byref(h)) == 10001 and b"multiple of 4" in lib.nerfb200_last_error()
+    assert not h.value
+    assert lib.nerfb200_peer_allreduce(None, None) == 10001
+    assert lib.nerfb200_peer_allreduce_adam(None, 4, None, None, None, 0, None, None) == 10001
+    assert lib.nerfb200_peer_destroy(None) == 0
     assert lib.nerfb200_mlp_stash_bytes(10, 0) == 10 * (63 + 27 + 8 * 256 + 256 + 128 + 3 + 1) * 4
 
 

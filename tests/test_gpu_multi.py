@@ -64,6 +64,72 @@ def _worker(rank, world, port, out):
             tn.train_step(((ro, rd, near, far), (rgb[lo:hi].cuda(),)))
         res[f"params_{prec}_{rank}"] = tn.flat_params.cpu().numpy()
         res[f"loss_{prec}_{rank}"] = float(tn.last_loss.item())
+    # ---- the gradient exchange over peer memory (csrc/peer.cu), on its own: 3 exchanges eagerly, then 3 replays of a
+    # captured launch; every rank must end up with the same, exact rank-ordered sum
+    import ctypes as C
+    from nerf_tf2_b200 import _lib
+    lib = _lib.load()
+    n = 4 * 100003                                         # slices of unequal length, not a multiple of the CTA size
+    h = C.c_void_p()
+    _lib.check(lib.nerfb200_peer_create(world, rank, n, C.byref(h)), "peer_create")
+    handle = C.create_string_buffer(64)
+    _lib.check(lib.nerfb200_peer_handle(h, handle), "peer_handle")
+    mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device="cuda")
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    _lib.check(lib.nerfb200_peer_connect(h, torch.stack(allh).cpu().numpy().tobytes()), "peer_connect")
+    addr = C.c_void_p()
+    _lib.check(lib.nerfb200_peer_buffer(h, C.byref(addr)), "peer_buffer")
+    buf = torch.as_tensor(nb.model._DeviceFloats(addr.value, n), device="cuda")
+    vals = [torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    def want(k):                                           # the sum in rank order, as the kernel forms it
+        w = vals[0] * k
+        for r in range(1, world):
+            w = w + vals[r] * k
+        return w
+    exch_ok = True
+    for it in range(3):
+        buf.copy_(vals[rank] * (it + 1))
+        _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")
+        exch_ok &= bool(torch.equal(buf.cpu(), want(it + 1)))
+    g = torch.cuda.CUDAGraph()
+    src = torch.empty(n, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        buf.copy_(src)
+        _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")
+    for it in range(3):
+        src.copy_(vals[rank] * (it + 5))
+        g.replay()
+        exch_ok &= bool(torch.equal(buf.cpu(), want(it + 5)))
+    st = C.c_int(-1)
+    _lib.check(lib.nerfb200_peer_status(h, C.byref(st)), "peer_status")
+    res[f"exchange_ok_{rank}"] = exch_ok and st.value == 0
+    del g, buf
+    torch.cuda.synchronize(); dist.barrier()
+    _lib.check(lib.nerfb200_peer_disconnect(h), "peer_disconnect")
+    dist.barrier()
+    _lib.check(lib.nerfb200_peer_destroy(h), "peer_destroy")
+    # ---- the same data-parallel steps under the other schedules: NCCL all-reduce instead of the peer kernel; the peer
+    # exchange with a separate Adam launch; the whole step as a CUDA graph. With two ranks a sum has one order, so all of
+    # them must leave bit-identical parameters.
+    lo, hi = nb.dist.shard_range(B, rank, world)
+    ro, rd = nb.ray_utils.get_rays_at(H, W, sc.K, sc.poses[0], ids[lo:hi].cuda())
+    near = torch.full((hi - lo, 1), sc.near, device="cuda"); far = torch.full((hi - lo, 1), sc.far, device="cuda")
+    batch = ((ro, rd, near, far), (rgb[lo:hi].cuda(),))
+    for name, kw in (("peer_fused", {}), ("nccl", {"peer_exchange": False}), ("peer_separate_adam", {"fuse": False}),
+                     ("peer_graph", {"graph": True})):
+        tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision="bf16", train_precision="bf16",
+                            seed=4, rng_seed=9, cuda_graph=kw.get("graph", False))
+        tn.set_distributed(peer_exchange=kw.get("peer_exchange", True))
+        tn.fuse_exchange_adam = kw.get("fuse", True)
+        res[f"sched_{name}_peer_{rank}"] = tn._peer is not None
+        for _ in range(5):
+            tn.train_step(batch)
+        res[f"sched_{name}_captured_{rank}"] = any("graph" in st for st in tn._graphs.values())
+        res[f"sched_{name}_{rank}"] = tn.flat_params.cpu().numpy()
+        res[f"sched_{name}_loss_{rank}"] = float(tn.last_loss.item())
+        tn.close_distributed()
     out[rank] = res
     dist.destroy_process_group()
 
@@ -107,3 +173,13 @@ def test_two_rank_sharded_render_and_data_parallel_step_equal_single_gpu():
         lim = 2e-6 if prec == "fp32" else 2e-5
         assert np.abs(p1 - r0[f"params_{prec}_0"]).max() <= lim, (prec, np.abs(p1 - r0[f"params_{prec}_0"]).max())
         assert abs(float(tn.last_loss.item()) - r0[f"loss_{prec}_0"]) <= 1e-5 * abs(r0[f"loss_{prec}_0"])
+    # the peer-memory exchange: exact sums on both ranks, eagerly and from a replayed graph
+    assert r0["exchange_ok_0"] and r1["exchange_ok_1"]
+    # every schedule of the data-parallel step leaves the same parameters, on both ranks
+    assert r0["sched_peer_fused_peer_0"] and r1["sched_peer_fused_peer_1"], "the peer exchange was not set up"
+    assert not r0["sched_nccl_peer_0"] and r0["sched_peer_graph_captured_0"] and r1["sched_peer_graph_captured_1"]
+    ref = r0["sched_peer_fused_0"]
+    for name in ("peer_fused", "nccl", "peer_separate_adam", "peer_graph"):
+        assert np.array_equal(r0[f"sched_{name}_0"], r1[f"sched_{name}_1"]), name
+        assert np.array_equal(r0[f"sched_{name}_0"], ref), (name, np.abs(r0[f"sched_{name}_0"] - ref).max())
+        assert r0[f"sched_{name}_loss_0"] == r0["sched_peer_fused_loss_0"], name

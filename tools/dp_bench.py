@@ -1,5 +1,6 @@
 """Developer tool (torchrun, N GPUs): the data-parallel training step under different schedules --
-eager / CUDA graph, all-reduce of the coarse half overlapped with the fine backward or not. (Leaving 4-16 SMs of the
+eager / CUDA graph, the gradient exchange by the library's peer-memory kernel (fused with Adam or not) or by NCCL
+(all-reduce of the coarse half overlapped with the fine backward or not). (Leaving 4-16 SMs of the
 fine backward free for NCCL was measured too, profiles/r2k_dp_n8.json: no gain -- the option was removed again.)
 usage: torchrun --nproc-per-node N tools/dp_bench.py [steps]"""
 import json
@@ -27,16 +28,19 @@ near = torch.full((B, 1), sc.near, device=dev); far = torch.full((B, 1), sc.far,
 rgb = torch.rand((B, 3), device=dev)
 batch = ((ro, rd, near, far), (rgb,))
 res = {}
-for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserve=0)),
-                 ("eager_overlap", dict(graph=False, overlap=True, reserve=0)),
-                 ("graph", dict(graph=True, overlap=False, reserve=0)),
-                 ("graph_overlap", dict(graph=True, overlap=True, reserve=0)),
-                 ("no_allreduce_graph", dict(graph=True, overlap=False, reserve=0, dist=False))):
+for name, kw in (("nccl_eager_overlap", dict(graph=False, overlap=True, peer=False)),
+                 ("nccl_graph", dict(graph=True, overlap=False, peer=False)),
+                 ("nccl_graph_overlap", dict(graph=True, overlap=True, peer=False)),
+                 ("peer_eager", dict(graph=False, peer=True)),
+                 ("peer_graph_separate_adam", dict(graph=True, peer=True, fuse=False)),
+                 ("peer_graph", dict(graph=True, peer=True)),
+                 ("no_exchange_graph", dict(graph=True, dist=False))):
     tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}), precision="bf16", train_precision="bf16", cuda_graph=kw["graph"],
                         precise_last=False)
     if kw.get("dist", True):
-        tn.set_distributed()
-    tn.overlap_allreduce = kw["overlap"]
+        tn.set_distributed(peer_exchange=kw.get("peer", True))
+    tn.overlap_allreduce = kw.get("overlap", True)
+    tn.fuse_exchange_adam = kw.get("fuse", True)
     tn.train_step(batch)
     # after ONE step the schedules may differ by fp32 summation order only (NCCL reduces a buffer split in two in a
     # different rank order than the same buffer in one piece); later steps amplify that chaotically
@@ -57,7 +61,9 @@ for name, kw in (("eager_one_allreduce", dict(graph=False, overlap=False, reserv
     ms = nb.dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
     res[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "captured": captured, "loss": float(tn.last_loss.item()),
                  "param_sum": float(tn.flat_params.double().sum().item()), "max_param_diff_after_step_1_vs_first_schedule": step1_diff}
+    res[name]["peer_exchange"] = tn._peer is not None
     tn.release_cuda_graphs()
+    tn.close_distributed()
     del tn
 res.pop("ref_first", None)
 if rank == 0:
