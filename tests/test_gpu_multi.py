@@ -182,4 +182,5 @@ def test_two_rank_sharded_render_and_data_parallel_step_equal_single_gpu():
     for name in ("peer_fused", "nccl", "peer_separate_adam", "peer_graph"):
         assert np.array_equal(r0[f"sched_{name}_0"], r1[f"sched_{name}_1"]), name
         assert np.array_equal(r0[f"sched_{name}_0"], ref), (name, np.abs(r0[f"sched_{name}_0"] - ref).max())
-        assert r0[f"sched_{name}_loss_0"] == r0["sched_peer_fused_loss_0"], name
+        # (the loss is a sum of float atomics over the CTAs of the loss kernel: equal to rounding, not bit for bit)
+        assert abs(r0[f"sched_{name}_loss_0"] - r0["sched_peer_fused_loss_0"]) <= 1e-6 * r0["sched_peer_fused_loss_0"], name

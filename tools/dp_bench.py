@@ -66,8 +66,51 @@ for name, kw in (("nccl_eager_overlap", dict(graph=False, overlap=True, peer=Fal
     tn.close_distributed()
     del tn
 res.pop("ref_first", None)
+
+# ---- the exchange alone, back to back on the 4.77 MB gradient buffer: the library's peer kernel vs NCCL
+import ctypes as C
+from nerf_tf2_b200 import _lib
+lib = _lib.load()
+n = _lib.PARAMS_TOTAL + 4
+h = C.c_void_p()
+_lib.check(lib.nerfb200_peer_create(world, rank, n, C.byref(h)), "peer_create")
+handle = C.create_string_buffer(64)
+_lib.check(lib.nerfb200_peer_handle(h, handle), "peer_handle")
+mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=dev)
+allh = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(allh, mine)
+_lib.check(lib.nerfb200_peer_connect(h, torch.stack(allh).cpu().numpy().tobytes()), "peer_connect")
+nccl_buf = torch.zeros(n, device=dev)
+opt = [torch.zeros(n - 4, device=dev) for _ in range(3)]
+
+
+def alone(fn, iters=300):
+    for _ in range(20):
+        fn()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    return nb.dist.max_over_ranks(e0.elapsed_time(e1), dev) / iters * 1e3
+
+
+exch = {"buffer_bytes": 4 * n,
+        "peer_kernel_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")),
+        "peer_kernel_with_adam_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce_adam(
+            h, n - 4, _lib.ptr(opt[0]), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None, _lib.stream_ptr()), "peer_allreduce_adam")),
+        "adam_kernel_alone_us": alone(lambda: _lib.check(lib.nerfb200_adam_step(
+            n - 4, _lib.ptr(opt[0]), _lib.ptr(nccl_buf), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None, _lib.stream_ptr()), "adam_step")),
+        "nccl_all_reduce_us": alone(lambda: dist.all_reduce(nccl_buf))}
+torch.cuda.synchronize(); dist.barrier()
+_lib.check(lib.nerfb200_peer_disconnect(h), "peer_disconnect")
+dist.barrier()
+_lib.check(lib.nerfb200_peer_destroy(h), "peer_destroy")
 if rank == 0:
-    print(json.dumps({"world": world, "rays_per_gpu": B, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "results": res}), flush=True)
+    print(json.dumps({"world": world, "rays_per_gpu": B, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "results": res,
+                      "exchange_alone": exch}), flush=True)
 dist.barrier()
 sys.stdout.flush()
 os._exit(0)
