@@ -239,7 +239,15 @@ NERFB200_API int nerfb200_step_advance(int64_t* step_state /* device int64[2] */
  *   peer_allreduce_adam  the same exchange followed, in the same launch, by nerfb200_adam_step over the first n
  *                 floats of the summed buffer (params/m/v: local, 16-byte aligned, n a multiple of 4): identical
  *                 arithmetic to peer_allreduce + adam_step.
+ *   peer_attach   instead of create/handle/connect, for a caller that has ALREADY mapped the ranks' blocks (here:
+ *                 torch symmetric memory): `blocks` = world device pointers, the block of every rank as mapped in
+ *                 this process, each 4096 header bytes (zeroed by the caller) + n_floats floats; `multicast_block` =
+ *                 the same block through an NVSwitch multicast (NVLS) mapping, or NULL. With a multicast mapping
+ *                 the slice is summed by the switch (multimem.ld_reduce) and replicated by the switch (multimem.st):
+ *                 1/world of the NVLink traffic; the order of that sum is the switch's, identical on all ranks.
  * Flags carry an epoch kept in device memory, so both launches can be captured in a CUDA graph and replayed. */
+NERFB200_API int nerfb200_peer_attach(int world, int rank, int64_t n_floats, void* const* blocks, void* multicast_block,
+                                      nerfb200_peer** peer);
 NERFB200_API int nerfb200_peer_create(int world, int rank, int64_t n_floats, nerfb200_peer** peer);
 NERFB200_API int nerfb200_peer_buffer(nerfb200_peer* peer, float** buffer);
 NERFB200_API int nerfb200_peer_handle(nerfb200_peer* peer, unsigned char* handle64);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "nerfb200_adam_step": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nerfb200_step_advance": (_i32, [_vp, _vp]),
     "nerfb200_peer_create": (_i32, [_i32, _i32, _i64, C.POINTER(_vp)]),
+    "nerfb200_peer_attach": (_i32, [_i32, _i32, _i64, C.POINTER(_vp), _vp, C.POINTER(_vp)]),
     "nerfb200_peer_buffer": (_i32, [_vp, C.POINTER(_vp)]),
     "nerfb200_peer_handle": (_i32, [_vp, C.c_char_p]),
     "nerfb200_peer_connect": (_i32, [_vp, C.c_char_p]),

@@ -47,6 +47,7 @@ struct AdamArgs {
 
 struct PeerParams {
     uint8_t* base[kPeerMaxWorld];         // every rank's block; base[rank] is local memory
+    uint8_t* mc;                          // the same block through an NVSwitch multicast mapping (NVLS), or NULL
     int world, rank;
     int64_t n4;                           // 16-byte units exchanged
     unsigned long long timeout_ns;
@@ -69,6 +70,16 @@ __device__ __forceinline__ float4 ld_sys_f4(const float4* p) {     // never serv
 }
 __device__ __forceinline__ void st_sys_f4(float4* p, float4 v) {
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// NVLS: one load returns the SUM of the addressed 16 bytes over every GPU of the multicast group (the switch reduces),
+// one store writes them into every GPU's copy (the switch replicates)
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float4* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_f4(float4* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -111,18 +122,24 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const Peer
     // ---- reduce + broadcast this rank's slice
     const int64_t per = (P.n4 + P.world - 1) / P.world;
     const int64_t lo = per * P.rank, hi = (lo + per < P.n4) ? lo + per : P.n4;
-    for (int64_t i = lo + (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; i < hi; i += (int64_t)gridDim.x * kPeerThreads) {
-        float4 v[kPeerMaxWorld];
+    if (P.mc) {          // NVLS: the switch sums the slice and replicates the result (the order of the sum is the switch's)
+        float4* mc = reinterpret_cast<float4*>(P.mc + kPeerHeaderBytes);
+        for (int64_t i = lo + (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; i < hi; i += (int64_t)gridDim.x * kPeerThreads)
+            multimem_st_f4(mc + i, multimem_ld_reduce_f4(mc + i));
+    } else {
+        for (int64_t i = lo + (int64_t)blockIdx.x * kPeerThreads + threadIdx.x; i < hi; i += (int64_t)gridDim.x * kPeerThreads) {
+            float4 v[kPeerMaxWorld];
 #pragma unroll
-        for (int p = 0; p < kPeerMaxWorld; ++p)
-            if (p < P.world) v[p] = ld_sys_f4(reinterpret_cast<const float4*>(P.base[p] + kPeerHeaderBytes) + i);
-        float4 s = v[0];
+            for (int p = 0; p < kPeerMaxWorld; ++p)
+                if (p < P.world) v[p] = ld_sys_f4(reinterpret_cast<const float4*>(P.base[p] + kPeerHeaderBytes) + i);
+            float4 s = v[0];
 #pragma unroll
-        for (int p = 1; p < kPeerMaxWorld; ++p)
-            if (p < P.world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+            for (int p = 1; p < kPeerMaxWorld; ++p)
+                if (p < P.world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
 #pragma unroll
-        for (int p = 0; p < kPeerMaxWorld; ++p)
-            if (p < P.world) st_sys_f4(reinterpret_cast<float4*>(P.base[p] + kPeerHeaderBytes) + i, s);
+            for (int p = 0; p < kPeerMaxWorld; ++p)
+                if (p < P.world) st_sys_f4(reinterpret_cast<float4*>(P.base[p] + kPeerHeaderBytes) + i, s);
+        }
     }
     __threadfence_system();          // this thread's peer stores are performed before ...
     __syncthreads();
@@ -172,8 +189,10 @@ using namespace nb;
 struct nerfb200_peer {
     int world = 0, rank = 0, device = 0, connected = 0;
     int timeout_s = 120;              // how long a rank waits for its peers inside the kernel before it traps
+    int owned = 1;                    // the blocks were allocated / mapped by this library (CUDA IPC)
     int64_t n = 0;
     uint8_t* base[kPeerMaxWorld] = {};
+    uint8_t* mc = nullptr;
 };
 
 extern "C" {
@@ -202,6 +221,28 @@ int nerfb200_peer_create(int world, int rank, int64_t n_floats, nerfb200_peer** 
     return 0;
 }
 
+int nerfb200_peer_attach(int world, int rank, int64_t n_floats, void* const* blocks, void* multicast_block, nerfb200_peer** peer) {
+    NB_CHECK_ARG(peer != nullptr, "peer_attach: NULL output");
+    *peer = nullptr;
+    NB_CHECK_ARG(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "peer_attach: world must be in [1,%d] and rank in [0,world)", kPeerMaxWorld);
+    NB_CHECK_ARG(n_floats > 0 && n_floats % 4 == 0 && blocks, "peer_attach: the exchanged buffer must be a positive multiple of 4 floats");
+    for (int r = 0; r < world; ++r)
+        NB_CHECK_ARG(blocks[r] && ((uintptr_t)blocks[r] & 15) == 0, "peer_attach: block %d is NULL or not 16-byte aligned", r);
+    NB_CHECK_ARG(((uintptr_t)multicast_block & 15) == 0, "peer_attach: multicast block not 16-byte aligned");
+    nerfb200_peer* p = new nerfb200_peer();
+    p->world = world; p->rank = rank; p->n = n_floats; p->owned = 0; p->connected = 1;
+    p->mc = (uint8_t*)multicast_block;
+    for (int r = 0; r < world; ++r) p->base[r] = (uint8_t*)blocks[r];
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e != cudaSuccess) {
+        set_error("peer_attach: %s", cudaGetErrorString(e));
+        delete p;
+        return (int)e;
+    }
+    *peer = p;
+    return 0;
+}
+
 int nerfb200_peer_buffer(nerfb200_peer* peer, float** buffer) {
     NB_CHECK_ARG(peer && buffer, "peer_buffer: NULL argument");
     *buffer = reinterpret_cast<float*>(peer->base[peer->rank] + kPeerHeaderBytes);
@@ -209,7 +250,7 @@ int nerfb200_peer_buffer(nerfb200_peer* peer, float** buffer) {
 }
 
 int nerfb200_peer_handle(nerfb200_peer* peer, unsigned char* handle64) {
-    NB_CHECK_ARG(peer && handle64, "peer_handle: NULL argument");
+    NB_CHECK_ARG(peer && handle64 && peer->owned, "peer_handle: NULL argument, or a handle attached to the caller's memory");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
     cudaIpcMemHandle_t h;
     NB_CUDA(cudaIpcGetMemHandle(&h, peer->base[peer->rank]));
@@ -219,7 +260,7 @@ int nerfb200_peer_handle(nerfb200_peer* peer, unsigned char* handle64) {
 
 int nerfb200_peer_connect(nerfb200_peer* peer, const unsigned char* handles) {
     NB_CHECK_ARG(peer && handles, "peer_connect: NULL argument");
-    NB_CHECK_ARG(!peer->connected, "peer_connect: already connected");
+    NB_CHECK_ARG(!peer->connected && peer->owned, "peer_connect: already connected");
     int dev = -1;
     NB_CUDA(cudaGetDevice(&dev));
     NB_CHECK_ARG(dev == peer->device, "peer_connect: created on device %d, current device is %d", peer->device, dev);
@@ -253,6 +294,7 @@ static int peer_launch(nerfb200_peer* peer, const AdamArgs* ad, void* stream) {
     NB_CHECK_ARG(dev == peer->device, "peer_allreduce: created on device %d, current device is %d", peer->device, dev);
     PeerParams P = {};
     for (int r = 0; r < peer->world; ++r) P.base[r] = peer->base[r];
+    P.mc = peer->mc;
     P.world = peer->world; P.rank = peer->rank; P.n4 = peer->n / 4;
     P.timeout_ns = (unsigned long long)peer->timeout_s * 1000000000ull;
     P.adam = ad ? 1 : 0;
@@ -300,7 +342,7 @@ int nerfb200_peer_status(nerfb200_peer* peer, int* status) {
 
 int nerfb200_peer_disconnect(nerfb200_peer* peer) {
     NB_CHECK_ARG(peer != nullptr, "peer_disconnect: NULL handle");
-    for (int r = 0; r < peer->world; ++r) {
+    for (int r = 0; r < peer->world && peer->owned; ++r) {
         if (r == peer->rank || !peer->base[r]) continue;
         cudaIpcCloseMemHandle(peer->base[r]);
         peer->base[r] = nullptr;
@@ -312,7 +354,7 @@ int nerfb200_peer_disconnect(nerfb200_peer* peer) {
 int nerfb200_peer_destroy(nerfb200_peer* peer) {
     if (!peer) return 0;
     nerfb200_peer_disconnect(peer);
-    if (peer->base[peer->rank]) cudaFree(peer->base[peer->rank]);
+    if (peer->owned && peer->base[peer->rank]) cudaFree(peer->base[peer->rank]);
     delete peer;
     return 0;
 }

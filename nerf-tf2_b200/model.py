@@ -279,6 +279,9 @@ class NeRF:
         self._peer_owner = None
         self._peer = None                 # nerfb200_peer handle: the gradient exchange over NVLink peer memory
         self.fuse_exchange_adam = True    # ... with the Adam step in the same launch
+        self.peer_mode = None             # "nvls" (switch reduces/replicates), "symm-p2p" or "ipc" (unicast loads/stores)
+        self.peer_symmetric_memory = True   # map the blocks through torch symmetric memory (else: the library's CUDA IPC)
+        self.peer_multicast = True        # use the NVLS multicast mapping when symmetric memory provides one
         self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
         self.graph_overlap_allreduce = True   # the same fork/join inside a captured step
         self.fused_forward = True         # forward()/predict()/render: the whole march as one C-ABI call (nerfb200_forward)
@@ -323,46 +326,79 @@ class NeRF:
 
     @_on_device
     def _setup_peer_exchange(self):
+        """Maps the ranks' gradient blocks into each other. First choice: torch symmetric memory (plumbing: it allocates
+        the block, exchanges the handles and, on an NVSwitch box, binds an NVLS multicast mapping) handed to
+        nerfb200_peer_attach; second: the library's own CUDA-IPC mapping (nerfb200_peer_create/handle/connect, unicast
+        loads and stores). Every decision is agreed on by all ranks before the next collective step."""
         import torch.distributed as dist
         import warnings
         lib, W, n = load(), self.world_size, PARAMS_TOTAL + 4
-        h, why = C.c_void_p(), ""
-        handle = C.create_string_buffer(64)
-        ok = W <= 8
-        if not ok:
-            why = "more than 8 ranks"
-        if ok and lib.nerfb200_peer_create(W, self.rank, n, C.byref(h)) != 0:
-            ok, why = False, lib.nerfb200_last_error().decode("utf-8", "replace")
-        if ok and lib.nerfb200_peer_handle(h, handle) != 0:
-            ok, why = False, lib.nerfb200_last_error().decode("utf-8", "replace")
-        # the 64-byte handles (+ one "so far so good" byte) go round by NCCL; every rank must take the same decision
-        mine = torch.tensor(list(handle.raw) + [int(ok)], dtype=torch.uint8, device=self.device)
-        gathered = [torch.empty_like(mine) for _ in range(W)]
-        dist.all_gather(gathered, mine, group=self.process_group)
-        blob = torch.stack(gathered).cpu().numpy()
-        buf = None
-        if ok and bool(blob[:, 64].all()):
-            if lib.nerfb200_peer_connect(h, blob[:, :64].tobytes()) != 0:
-                ok, why = False, lib.nerfb200_last_error().decode("utf-8", "replace")
-            else:
-                try:
-                    addr = C.c_void_p()
-                    check(lib.nerfb200_peer_buffer(h, C.byref(addr)), "peer_buffer")
-                    buf = torch.as_tensor(_DeviceFloats(addr.value, n), device=self.device)
-                    assert buf.data_ptr() == addr.value and buf.dtype == torch.float32 and buf.numel() == n
-                except Exception as ex:          # torch could not wrap the library's memory
-                    ok, why, buf = False, f"{type(ex).__name__}: {ex}", None
-        else:
-            ok = False
-        agreed = torch.tensor([int(ok)], dtype=torch.int32, device=self.device)
-        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.process_group)
-        if not int(agreed.item()):
-            # (the block, if any, is left allocated: a peer may have mapped it already)
-            warnings.warn("peer-memory gradient exchange unavailable on some rank"
-                          + (f" (this rank: {why})" if why else "") + "; using the NCCL all-reduce")
+
+        def agreed(ok):
+            flag = torch.tensor([int(bool(ok))], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.process_group)
+            return bool(int(flag.item()))
+
+        if W > 8:
+            warnings.warn("peer-memory gradient exchange: more than 8 ranks; using the NCCL all-reduce")
             return
+        h, buf, keep, mode, why = C.c_void_p(), None, None, None, ""
+        # ---- 1. symmetric memory (+ NVLS multicast where the box has it)
+        block = None
+        if self.peer_symmetric_memory:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                block = symm_mem.empty(1024 + n, dtype=torch.float32, device=self.device)     # 4096 header bytes + floats
+                block.zero_()
+                torch.cuda.synchronize(self.device)
+            except Exception as ex:
+                block, why = None, f"symmetric memory: {type(ex).__name__}: {ex}"
+        if agreed(block is not None):
+            try:
+                hdl = symm_mem.rendezvous(block, self.process_group)
+                off = block.data_ptr() - int(hdl.buffer_ptrs[hdl.rank])
+                assert hdl.world_size == W and hdl.rank == self.rank and 0 <= off and off + block.numel() * 4 <= hdl.buffer_size
+                bases = (C.c_void_p * W)(*[int(p) + off for p in hdl.buffer_ptrs])
+                mc = int(hdl.multicast_ptr) + off if (self.peer_multicast and int(hdl.multicast_ptr)) else 0
+                check(lib.nerfb200_peer_attach(W, self.rank, n, bases, C.c_void_p(mc), C.byref(h)), "peer_attach")
+                buf, keep, mode = block[1024:], (block, hdl), ("nvls" if mc else "symm-p2p")
+            except Exception as ex:
+                h, buf, why = C.c_void_p(), None, f"symmetric memory: {type(ex).__name__}: {ex}"
+            if agreed(buf is not None):
+                dist.barrier(group=self.process_group)          # every header is zeroed and mapped before the first flag
+            else:
+                h, buf = C.c_void_p(), None
+        # ---- 2. the library's own CUDA-IPC mapping
+        if buf is None:
+            handle = C.create_string_buffer(64)
+            ok = lib.nerfb200_peer_create(W, self.rank, n, C.byref(h)) == 0 and lib.nerfb200_peer_handle(h, handle) == 0
+            if not ok:
+                why = lib.nerfb200_last_error().decode("utf-8", "replace")
+            mine = torch.tensor(list(handle.raw) + [int(ok)], dtype=torch.uint8, device=self.device)
+            gathered = [torch.empty_like(mine) for _ in range(W)]
+            dist.all_gather(gathered, mine, group=self.process_group)       # the 64-byte handles go round by NCCL
+            blob = torch.stack(gathered).cpu().numpy()
+            if ok and bool(blob[:, 64].all()):
+                if lib.nerfb200_peer_connect(h, blob[:, :64].tobytes()) != 0:
+                    ok, why = False, lib.nerfb200_last_error().decode("utf-8", "replace")
+                else:
+                    try:
+                        addr = C.c_void_p()
+                        check(lib.nerfb200_peer_buffer(h, C.byref(addr)), "peer_buffer")
+                        buf = torch.as_tensor(_DeviceFloats(addr.value, n), device=self.device)
+                        assert buf.data_ptr() == addr.value and buf.dtype == torch.float32 and buf.numel() == n
+                        keep, mode = buf, "ipc"
+                    except Exception as ex:          # torch could not wrap the library's memory
+                        ok, why, buf = False, f"{type(ex).__name__}: {ex}", None
+            else:
+                ok = False
+            if not agreed(ok and buf is not None):
+                # (the block, if any, stays allocated: a peer may have mapped it already)
+                warnings.warn("peer-memory gradient exchange unavailable on some rank"
+                              + (f" (this rank: {why})" if why else "") + "; using the NCCL all-reduce")
+                return
         buf.copy_(self._grad_buf)
-        self._peer, self._peer_owner = h, buf
+        self._peer, self._peer_owner, self.peer_mode = h, keep, mode
         self._grad_buf = buf
         self.flat_grads = self._grad_buf[:PARAMS_TOTAL]
         self._graphs.clear()              # captured steps hold the old gradient buffer
@@ -386,6 +422,7 @@ class NeRF:
             check(load().nerfb200_peer_disconnect(self._peer), "peer_disconnect")
             dist.barrier(group=self.process_group)
             check(load().nerfb200_peer_destroy(self._peer), "peer_destroy")
+        self.peer_mode = None
         self._peer = None
 
     def set_flat_params(self, flat):

@@ -14,6 +14,7 @@ sys.path.insert(0, ".")
 import nerf_tf2_b200 as nb
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+only_exchange = len(sys.argv) > 2 and sys.argv[2] == "exchange"      # skip the schedules, time the exchange alone
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 os.environ.setdefault("NCCL_DEBUG", "WARN")
@@ -34,9 +35,14 @@ for name, kw in (("nccl_eager_overlap", dict(graph=False, overlap=True, peer=Fal
                  ("peer_eager", dict(graph=False, peer=True)),
                  ("peer_graph_separate_adam", dict(graph=True, peer=True, fuse=False)),
                  ("peer_graph", dict(graph=True, peer=True)),
+                 ("peer_graph_unicast", dict(graph=True, peer=True, multicast=False)),
+                 ("peer_graph_ipc", dict(graph=True, peer=True, symm=False)),
                  ("no_exchange_graph", dict(graph=True, dist=False))):
+    if only_exchange:
+        break
     tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}), precision="bf16", train_precision="bf16", cuda_graph=kw["graph"],
                         precise_last=False)
+    tn.peer_symmetric_memory, tn.peer_multicast = kw.get("symm", True), kw.get("multicast", True)
     if kw.get("dist", True):
         tn.set_distributed(peer_exchange=kw.get("peer", True))
     tn.overlap_allreduce = kw.get("overlap", True)
@@ -61,25 +67,17 @@ for name, kw in (("nccl_eager_overlap", dict(graph=False, overlap=True, peer=Fal
     ms = nb.dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
     res[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "captured": captured, "loss": float(tn.last_loss.item()),
                  "param_sum": float(tn.flat_params.double().sum().item()), "max_param_diff_after_step_1_vs_first_schedule": step1_diff}
-    res[name]["peer_exchange"] = tn._peer is not None
+    res[name]["peer_exchange"] = tn.peer_mode
     tn.release_cuda_graphs()
     tn.close_distributed()
     del tn
 res.pop("ref_first", None)
 
-# ---- the exchange alone, back to back on the 4.77 MB gradient buffer: the library's peer kernel vs NCCL
-import ctypes as C
+# ---- the exchange alone, back to back on the 4.77 MB gradient buffer: the library's peer kernel (NVLS multicast, unicast over
+# symmetric memory, unicast over the library's own IPC mapping) vs NCCL
 from nerf_tf2_b200 import _lib
 lib = _lib.load()
 n = _lib.PARAMS_TOTAL + 4
-h = C.c_void_p()
-_lib.check(lib.nerfb200_peer_create(world, rank, n, C.byref(h)), "peer_create")
-handle = C.create_string_buffer(64)
-_lib.check(lib.nerfb200_peer_handle(h, handle), "peer_handle")
-mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=dev)
-allh = [torch.empty_like(mine) for _ in range(world)]
-dist.all_gather(allh, mine)
-_lib.check(lib.nerfb200_peer_connect(h, torch.stack(allh).cpu().numpy().tobytes()), "peer_connect")
 nccl_buf = torch.zeros(n, device=dev)
 opt = [torch.zeros(n - 4, device=dev) for _ in range(3)]
 
@@ -97,17 +95,22 @@ def alone(fn, iters=300):
     return nb.dist.max_over_ranks(e0.elapsed_time(e1), dev) / iters * 1e3
 
 
-exch = {"buffer_bytes": 4 * n,
-        "peer_kernel_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")),
-        "peer_kernel_with_adam_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce_adam(
-            h, n - 4, _lib.ptr(opt[0]), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None, _lib.stream_ptr()), "peer_allreduce_adam")),
-        "adam_kernel_alone_us": alone(lambda: _lib.check(lib.nerfb200_adam_step(
-            n - 4, _lib.ptr(opt[0]), _lib.ptr(nccl_buf), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None, _lib.stream_ptr()), "adam_step")),
-        "nccl_all_reduce_us": alone(lambda: dist.all_reduce(nccl_buf))}
-torch.cuda.synchronize(); dist.barrier()
-_lib.check(lib.nerfb200_peer_disconnect(h), "peer_disconnect")
-dist.barrier()
-_lib.check(lib.nerfb200_peer_destroy(h), "peer_destroy")
+exch = {"buffer_bytes": 4 * n}
+for label, symm, mcast in (("default", True, True), ("unicast", True, False), ("ipc", False, False)):
+    tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}), precision="bf16", train_precision="bf16", precise_last=False)
+    tn.peer_symmetric_memory, tn.peer_multicast = symm, mcast
+    tn.set_distributed()
+    tn._grad_buf.zero_()
+    h = tn._peer
+    exch[label] = {"mode": tn.peer_mode,
+                   "peer_kernel_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")),
+                   "peer_kernel_with_adam_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce_adam(
+                       h, n - 4, _lib.ptr(opt[0]), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None, _lib.stream_ptr()), "peer_allreduce_adam"))}
+    tn.close_distributed()
+    del tn
+exch["adam_kernel_alone_us"] = alone(lambda: _lib.check(lib.nerfb200_adam_step(
+    n - 4, _lib.ptr(opt[0]), _lib.ptr(nccl_buf), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None, _lib.stream_ptr()), "adam_step"))
+exch["nccl_all_reduce_us"] = alone(lambda: dist.all_reduce(nccl_buf))
 if rank == 0:
     print(json.dumps({"world": world, "rays_per_gpu": B, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "results": res,
                       "exchange_alone": exch}), flush=True)
