@@ -141,11 +141,11 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const Peer
                 if (p < P.world) st_sys_f4(reinterpret_cast<float4*>(P.base[p] + kPeerHeaderBytes) + i, s);
         }
     }
-    __threadfence_system();          // this thread's peer stores are performed before ...
-    __syncthreads();
-    if (threadIdx.x == 0) {          // ... the CTA is counted as done
+    __syncthreads();                 // the CTA's peer stores happen before thread 0's fence (cumulativity), which is
+    if (threadIdx.x == 0) {          // before the CTA is counted as done
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
         s_last = (atomicAdd(&me->done_ctas, 1u) == gridDim.x - 1) ? 1 : 0;
-        __threadfence_system();
+        asm volatile("fence.acq_rel.sys;" ::: "memory");       // the last CTA has seen every other CTA's stores
     }
     __syncthreads();
 

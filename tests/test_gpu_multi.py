@@ -118,10 +118,11 @@ def _worker(rank, world, port, out):
     near = torch.full((hi - lo, 1), sc.near, device="cuda"); far = torch.full((hi - lo, 1), sc.far, device="cuda")
     batch = ((ro, rd, near, far), (rgb[lo:hi].cuda(),))
     for name, kw in (("peer_fused", {}), ("nccl", {"peer_exchange": False}), ("peer_separate_adam", {"fuse": False}),
-                     ("peer_graph", {"graph": True}), ("peer_unicast", {"multicast": False}), ("peer_ipc", {"symm": False})):
+                     ("peer_graph", {"graph": True}), ("peer_multicast", {"multicast": True}), ("peer_unicast", {"multicast": False}),
+                     ("peer_ipc", {"symm": False})):
         tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}, perturb=True), precision="bf16", train_precision="bf16",
                             seed=4, rng_seed=9, cuda_graph=kw.get("graph", False))
-        tn.peer_symmetric_memory, tn.peer_multicast = kw.get("symm", True), kw.get("multicast", True)
+        tn.peer_symmetric_memory, tn.peer_multicast = kw.get("symm", True), kw.get("multicast", None)
         tn.set_distributed(peer_exchange=kw.get("peer_exchange", True))
         tn.fuse_exchange_adam = kw.get("fuse", True)
         res[f"sched_{name}_peer_{rank}"] = tn.peer_mode
@@ -183,7 +184,7 @@ def test_two_rank_sharded_render_and_data_parallel_step_equal_single_gpu():
     print("peer modes:", {k: v for k, v in r0.items() if k.startswith("sched_") and k.endswith("_peer_0")})
     assert r0["sched_peer_ipc_peer_0"] == "ipc" and r0["sched_peer_unicast_peer_0"] in ("symm-p2p", "ipc")
     ref = r0["sched_peer_fused_0"]
-    for name in ("peer_fused", "nccl", "peer_separate_adam", "peer_graph", "peer_unicast", "peer_ipc"):
+    for name in ("peer_fused", "nccl", "peer_separate_adam", "peer_graph", "peer_multicast", "peer_unicast", "peer_ipc"):
         assert np.array_equal(r0[f"sched_{name}_0"], r1[f"sched_{name}_1"]), name
         assert np.array_equal(r0[f"sched_{name}_0"], ref), (name, np.abs(r0[f"sched_{name}_0"] - ref).max())
         # (the loss is a sum of float atomics over the CTAs of the loss kernel: equal to rounding, not bit for bit)

@@ -42,7 +42,7 @@ for name, kw in (("nccl_eager_overlap", dict(graph=False, overlap=True, peer=Fal
         break
     tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}), precision="bf16", train_precision="bf16", cuda_graph=kw["graph"],
                         precise_last=False)
-    tn.peer_symmetric_memory, tn.peer_multicast = kw.get("symm", True), kw.get("multicast", True)
+    tn.peer_symmetric_memory, tn.peer_multicast = kw.get("symm", True), kw.get("multicast", None)
     if kw.get("dist", True):
         tn.set_distributed(peer_exchange=kw.get("peer", True))
     tn.overlap_allreduce = kw.get("overlap", True)
@@ -96,7 +96,7 @@ def alone(fn, iters=300):
 
 
 exch = {"buffer_bytes": 4 * n}
-for label, symm, mcast in (("default", True, True), ("unicast", True, False), ("ipc", False, False)):
+for label, symm, mcast in (("multicast", True, True), ("unicast", True, False), ("ipc", False, False)):
     tn = nb.setup_model(nb.make_params({"system": {"white_bg": True}}), precision="bf16", train_precision="bf16", precise_last=False)
     tn.peer_symmetric_memory, tn.peer_multicast = symm, mcast
     tn.set_distributed()
