@@ -594,6 +594,27 @@ struct ReduceParams {
     int nsplit[kDwJobs];
     long long poff[kDwJobs], boff[kDwJobs];
 };
+// sum of one element over a job's K-splits, in split order (deterministic); the loads of up to eight splits are issued
+// together -- one load per iteration of a plain loop leaves a single request in flight per thread, and the launch
+// is then bound by 13 dependent trips to HBM (14.5 us for 39 MB) instead of by bandwidth
+__device__ __forceinline__ float fold_splits(const float* __restrict__ src, int nsplit, size_t stride) {
+    float s = 0.f;
+    int c = 0;
+    for (; c + 8 <= nsplit; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(src + (size_t)(c + q) * stride);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += v[q];
+    }
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = (c + q < nsplit) ? __ldg(src + (size_t)(c + q) * stride) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (c + q < nsplit) s += v[q];
+    return s;
+}
 __global__ void reduce_grads_kernel(const ReduceParams rp, const float* __restrict__ partial, float* __restrict__ G /* one model */) {
     const DwJob jb = rp.job[blockIdx.y];
     const int nsplit = rp.nsplit[blockIdx.y];
@@ -606,15 +627,11 @@ __global__ void reduce_grads_kernel(const ReduceParams rp, const float* __restri
     if (i < total) {
         const int m = i / jb.n_cols, n = i - m * jb.n_cols;
         const float* src = partial + rp.poff[blockIdx.y] + (size_t)m * N + jb.n_col0 + n;
-        float s = 0.f;
-        for (int c = 0; c < nsplit; ++c) s += src[(size_t)c * per_cta];
-        G[kernel_offset(jb.layer) + (size_t)(jb.k_row0 + m) * fan_out + n] += s;
+        G[kernel_offset(jb.layer) + (size_t)(jb.k_row0 + m) * fan_out + n] += fold_splits(src, nsplit, per_cta);
     } else if (jb.bias_layer >= 0 && i < total + jb.n_cols) {
         const int n = i - total;
         const float* src = partial + rp.boff[blockIdx.y] + jb.n_col0 + n;
-        float s = 0.f;
-        for (int c = 0; c < nsplit; ++c) s += src[(size_t)c * 256];
-        G[bias_offset(jb.bias_layer) + n] += s;
+        G[bias_offset(jb.bias_layer) + n] += fold_splits(src, nsplit, 256);
     }
 }
 
