@@ -590,7 +590,7 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
                             precise_last=False)
         if world > 1:
             tn.set_distributed(peer_exchange=peer)
-        used_peer = tn._peer is not None
+        used_peer = tn.peer_mode
         for _ in range(5):
             tn.train_step(batch)
         barrier()
@@ -622,9 +622,11 @@ def bench_train(nb, nerf, torch, dist, world, rank, dev, barrier, args):
     return {"metric": "train steps/s (4096-ray batch, coarse+fine fwd/bwd + Adam, data-parallel all-reduce)",
             "value": sps, "unit": "steps/s", "ms_per_step": ms / steps, "steps": steps, "precision": tp,
             "global_batch": B, "rays_per_gpu": Bl, "achieved_tflops": flop * sps / 1e12,
-            "gradient_exchange": (None if world == 1 else
-                                  "one kernel per rank over NVLink peer memory (reduce-scatter + all-gather by loads/stores, "
-                                  "fused with Adam; csrc/peer.cu)" if used_peer else "NCCL all-reduce"),
+            "gradient_exchange": (None if world == 1 else "NCCL all-reduce" if not used_peer else
+                                  {"kernel": "one launch per rank over NVLink peer memory, fused with Adam (csrc/peer.cu)",
+                                   "mapping": used_peer,
+                                   "data_path": ("NVLS: multimem.ld_reduce / multimem.st through the NVSwitch multicast mapping"
+                                                 if used_peer == "nvls" else "unicast peer loads / stores (reduce-scatter + all-gather)")}),
             "with_nccl_allreduce_instead": nccl,
             "frac_of_sustained_peak": flop * sps / 1e12 / (pk["tensor"] * world),
             "launch_mode": ("one CUDA graph per step (sampling, forwards, loss, backwards, all-reduce, Adam, repack)"
