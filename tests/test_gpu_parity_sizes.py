@@ -210,7 +210,7 @@ def test_forward_other_configurations_vs_oracle(cfg):
         assert np.abs(host(oc[k]) - pc[k]).max() <= lim and np.abs(host(of[k]) - pf[k]).max() <= lim, (cfg, k)
     # the flip-rate bound of the stated tolerance is for the BASELINE sample counts; with 32+64 samples the last
     # hierarchical sample moves further for the same 16-bit error of the coarse pass (measured: 2 of 300 rays with bf16,
-    # 0 with fp16, profiles/r2v_parity_other_cfg_32_64.json) -- there the bound is 1 %. In every configuration a
+    # 0 with fp16, profiles/r2z_parity_other_cfg_32_64.json) -- there the bound is 1 %. In every configuration a
     # flipped ray must sit on the jump: the oracle's own last-sample pre-activation within ON_JUMP_MARGIN of zero.
     rate = MAX_FLIP_RATE if cfg["Nc"] >= 64 else MAX_FLIP_RATE_COARSE_SAMPLING
     pre_last = (dbg["sigma_pre_last_c"], dbg["sigma_pre_last_f"])
