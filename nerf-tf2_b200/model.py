@@ -311,12 +311,14 @@ class NeRF:
         self.metrics = list(metrics) if metrics is not None else [ops.PSNRMetric()]
 
     def set_distributed(self, process_group=None, peer_exchange=True):
-        """Data-parallel training over torch.distributed (NCCL on GPUs): the 4096-ray batch is split across ranks and
-        the flat [gradient | loss] buffer is summed over the ranks once per step. `peer_exchange`
-        (default): the ranks map each other's gradient buffer over NVLink (CUDA IPC) and one kernel of this library
-        does the exchange -- fused with the Adam step -- instead of an NCCL all-reduce (csrc/peer.cu); NCCL then only
-        carries the 64-byte handles. Falls back to the NCCL all-reduce, with a warning, if the ranks cannot map each
-        other's memory (more than 8 ranks, several nodes, no peer access)."""
+        """Data-parallel training over torch.distributed (one process per GPU): the 4096-ray batch is split across the
+        ranks and the flat [gradient | loss] buffer is summed over the ranks once per step.
+        `peer_exchange` (default): the ranks map each other's gradient block over NVLink -- through torch symmetric
+        memory (with an NVLS multicast mapping on an NVSwitch box) or, failing that, the library's own CUDA-IPC
+        mapping -- and ONE kernel of this library per rank does the exchange, fused with the Adam step (csrc/peer.cu,
+        DESIGN.md 4.2c); NCCL then only carries the mapping handshake. Falls back to an NCCL all-reduce, with a warning,
+        if the ranks cannot map each other's memory (more than 8 ranks, several nodes, no peer access).
+        `peer_symmetric_memory` / `peer_multicast` (attributes, set before this call) select the mapping."""
         import torch.distributed as dist
         self.process_group = process_group if process_group is not None else dist.group.WORLD
         self.world_size = dist.get_world_size(self.process_group)
