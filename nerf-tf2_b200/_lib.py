@@ -62,6 +62,7 @@ SIGNATURES = {
     "nerfb200_peer_allreduce": (_i32, [_vp, _vp]),
     "nerfb200_peer_allreduce_adam": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nerfb200_peer_status": (_i32, [_vp, C.POINTER(_i32)]),
+    "nerfb200_peer_profile": (_i32, [_vp, C.POINTER(C.c_ulonglong)]),
     "nerfb200_peer_disconnect": (_i32, [_vp]),
     "nerfb200_peer_destroy": (_i32, [_vp]),
     "nerfb200_depth_type2": (_i32, [_i32, _i32, C.POINTER(_dbl), C.POINTER(_dbl), _dbl, _vp, _vp, _vp]),

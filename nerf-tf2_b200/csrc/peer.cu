@@ -35,7 +35,9 @@ struct PeerHeader {                       // at offset 0 of every rank's block; 
     uint32_t epoch;                       // exchanges completed by this rank
     uint32_t done_ctas;                   // CTAs of the running exchange that have finished their slice
     uint32_t status;                      // != 0: a wait timed out (the kernel traps right after setting it)
-};
+    uint32_t pad;
+    unsigned long long stamp[6];          // %globaltimer of the latest exchange (nerfb200_peer_profile): start, barrier A
+};                                        // passed, own slice done [CTA 0]; all CTAs done, barrier B passed, end [last CTA]
 static_assert(sizeof(PeerHeader) <= kPeerHeaderBytes, "header");
 
 struct AdamArgs {
@@ -112,12 +114,15 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const Peer
     if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(&me->epoch) + 1u;
     __syncthreads();
     const uint32_t epoch = s_epoch;
+    const bool stamper = blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamper) me->stamp[0] = global_ns();
 
     // ---- barrier A. The local gradient was written by earlier kernels of this stream: complete and visible in this
     // GPU's memory (where the peers' loads are served) when this kernel starts.
     if (blockIdx.x == 0 && (int)threadIdx.x < P.world)
         st_release_sys(&reinterpret_cast<PeerHeader*>(P.base[threadIdx.x])->arrive[0][P.rank], epoch);
     wait_flags(me, 0, P.world, epoch, P.timeout_ns);
+    if (stamper) me->stamp[1] = global_ns();
 
     // ---- reduce + broadcast this rank's slice
     const int64_t per = (P.n4 + P.world - 1) / P.world;
@@ -144,23 +149,26 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const Peer
     __syncthreads();                 // the CTA's peer stores happen before thread 0's fence (cumulativity), which is
     if (threadIdx.x == 0) {          // before the CTA is counted as done
         asm volatile("fence.acq_rel.sys;" ::: "memory");
+        if (stamper) me->stamp[2] = global_ns();
         s_last = (atomicAdd(&me->done_ctas, 1u) == gridDim.x - 1) ? 1 : 0;
         asm volatile("fence.acq_rel.sys;" ::: "memory");       // the last CTA has seen every other CTA's stores
     }
     __syncthreads();
 
     // ---- barrier B: the LAST CTA to finish tells every peer that this rank's slice has landed
+    if (s_last && threadIdx.x == 0) me->stamp[3] = global_ns();
     if (s_last && (int)threadIdx.x < P.world)
         st_release_sys(&reinterpret_cast<PeerHeader*>(P.base[threadIdx.x])->arrive[1][P.rank], epoch);
     if (!P.adam) {
         if (!s_last) return;
         wait_flags(me, 1, P.world, epoch, P.timeout_ns);      // the kernel ends when every peer's slice is here
-        if (threadIdx.x == 0) { me->done_ctas = 0u; me->epoch = epoch; }
+        if (threadIdx.x == 0) { me->stamp[4] = me->stamp[5] = global_ns(); me->done_ctas = 0u; me->epoch = epoch; }
         return;
     }
     // ---- fused Adam epilogue: every CTA needs the full sum (grid <= SM count: all CTAs are resident, none waits for a
     // CTA that cannot run)
     wait_flags(me, 1, P.world, epoch, P.timeout_ns);
+    if (s_last && threadIdx.x == 0) me->stamp[4] = global_ns();
     if (P.ad.step_dev) {      // device-resident iteration counter (CUDA-graph replays)
         if (threadIdx.x == 0) s_lr_t = adam_lr_t(P.ad.step_dev[0]);
         __syncthreads();
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const Peer
         adam_update(p.w, m.w, v.w, g.w, lr_t);
         m4[i] = m; v4[i] = v; p4[i] = p;
     }
-    if (s_last && threadIdx.x == 0) { me->done_ctas = 0u; me->epoch = epoch; }
+    if (s_last && threadIdx.x == 0) { me->stamp[5] = global_ns(); me->done_ctas = 0u; me->epoch = epoch; }
 }
 
 }  // namespace nb
@@ -337,6 +345,12 @@ int nerfb200_peer_status(nerfb200_peer* peer, int* status) {
     uint32_t s = 0;
     NB_CUDA(cudaMemcpy(&s, peer->base[peer->rank] + offsetof(PeerHeader, status), 4, cudaMemcpyDeviceToHost));
     *status = (int)s;
+    return 0;
+}
+
+int nerfb200_peer_profile(nerfb200_peer* peer, unsigned long long* ns6) {
+    NB_CHECK_ARG(peer && ns6, "peer_profile: NULL argument");
+    NB_CUDA(cudaMemcpy(ns6, peer->base[peer->rank] + offsetof(PeerHeader, stamp), 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 

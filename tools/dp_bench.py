@@ -75,6 +75,7 @@ res.pop("ref_first", None)
 
 # ---- the exchange alone, back to back on the 4.77 MB gradient buffer: the library's peer kernel (NVLS multicast, unicast over
 # symmetric memory, unicast over the library's own IPC mapping) vs NCCL
+import ctypes as C
 from nerf_tf2_b200 import _lib
 lib = _lib.load()
 n = _lib.PARAMS_TOTAL + 4
@@ -106,6 +107,23 @@ for label, symm, mcast in (("multicast", True, True), ("unicast", True, False), 
                    "peer_kernel_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")),
                    "peer_kernel_with_adam_us": alone(lambda: _lib.check(lib.nerfb200_peer_allreduce_adam(
                        h, n - 4, _lib.ptr(opt[0]), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None, _lib.stream_ptr()), "peer_allreduce_adam"))}
+    # where the time goes inside ONE exchange (the kernel's own %globaltimer stamps, per rank): the last of 20 back to back
+    for fused in (False, True):
+        for _ in range(20):
+            if fused:
+                _lib.check(lib.nerfb200_peer_allreduce_adam(h, n - 4, _lib.ptr(opt[0]), _lib.ptr(opt[1]), _lib.ptr(opt[2]), 0, None,
+                                                            _lib.stream_ptr()), "peer_allreduce_adam")
+            else:
+                _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")
+        torch.cuda.synchronize()
+        st = (C.c_ulonglong * 6)()
+        _lib.check(lib.nerfb200_peer_profile(h, st), "peer_profile")
+        mine_t = torch.tensor([float(st[i] - st[0]) / 1e3 for i in range(6)], device=dev)
+        allt = [torch.empty_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        exch[label]["stamps_us_with_adam" if fused else "stamps_us"] = {
+            "what": "per rank, us since kernel start: barrier A passed, own slice done (first CTA); all CTAs done, barrier B passed, end (last CTA)",
+            "ranks": [[round(float(x), 2) for x in t[1:].tolist()] for t in allt]}
     tn.close_distributed()
     del tn
 exch["adam_kernel_alone_us"] = alone(lambda: _lib.check(lib.nerfb200_adam_step(
