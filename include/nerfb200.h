@@ -258,8 +258,9 @@ NERFB200_API int nerfb200_peer_allreduce_adam(nerfb200_peer* peer, int64_t n, fl
                                  int64_t iterations, const int64_t* step_state, void* stream);
 NERFB200_API int nerfb200_peer_status(nerfb200_peer* peer, int* status /* 0, or the barrier (1/2) a wait timed out at */);
 /* diagnostic: %globaltimer (ns) of this rank's latest exchange -- start, barrier A passed, own slice done (first CTA);
- * all CTAs done, barrier B passed, end (last CTA). Synchronous copy: call it on an idle stream. */
-NERFB200_API int nerfb200_peer_profile(nerfb200_peer* peer, unsigned long long* ns6);
+ * all CTAs done, barrier B passed, end (last CTA); [6] = the first CTA's loads returned and stores issued, before its
+ * system fence. Synchronous copy: call it on an idle stream. */
+NERFB200_API int nerfb200_peer_profile(nerfb200_peer* peer, unsigned long long* ns7);
 NERFB200_API int nerfb200_peer_disconnect(nerfb200_peer* peer);   /* unmaps the other ranks' blocks */
 NERFB200_API int nerfb200_peer_destroy(nerfb200_peer* peer);      /* + frees this rank's block: only after EVERY rank has disconnected */
 

@@ -116,13 +116,13 @@ for label, symm, mcast in (("multicast", True, True), ("unicast", True, False), 
             else:
                 _lib.check(lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()), "peer_allreduce")
         torch.cuda.synchronize()
-        st = (C.c_ulonglong * 6)()
+        st = (C.c_ulonglong * 7)()
         _lib.check(lib.nerfb200_peer_profile(h, st), "peer_profile")
-        mine_t = torch.tensor([float(st[i] - st[0]) / 1e3 for i in range(6)], device=dev)
+        mine_t = torch.tensor([float(st[i] - st[0]) / 1e3 for i in (0, 1, 6, 2, 3, 4, 5)], device=dev)
         allt = [torch.empty_like(mine_t) for _ in range(world)]
         dist.all_gather(allt, mine_t)
         exch[label]["stamps_us_with_adam" if fused else "stamps_us"] = {
-            "what": "per rank, us since kernel start: barrier A passed, own slice done (first CTA); all CTAs done, barrier B passed, end (last CTA)",
+            "what": "per rank, us since kernel start: barrier A passed, loads back + stores issued, system fence done (first CTA); all CTAs done, barrier B passed, end (last CTA)",
             "ranks": [[round(float(x), 2) for x in t[1:].tolist()] for t in allt]}
     tn.close_distributed()
     del tn
