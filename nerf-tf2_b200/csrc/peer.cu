@@ -152,14 +152,17 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(const Peer
     // the slice needs; 592 fences and atomics instead of 146 cost 5 us).
     int64_t wk = (hi - lo + kPeerThreads - 1) / kPeerThreads;
     const unsigned working = (unsigned)(wk < 1 ? 1 : (wk > (int64_t)gridDim.x ? (int64_t)gridDim.x : wk));
-    __syncthreads();                 // the CTA's peer stores happen before thread 0's fence (cumulativity), which is
-    if (threadIdx.x == 0) {          // before the CTA is counted as done
+    __syncthreads();                 // the CTA's peer stores happen before thread 0's fence (cumulativity over the CTA
+    if (threadIdx.x == 0) {          // barrier), which is before the CTA is counted as done
         s_last = 0;
         if (blockIdx.x < working) {
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            // gpu scope: this fence and the counter order the CTAs of THIS GPU; the one system-scope release is the last
+            // CTA's flag store below, and it is cumulative over this chain (a system fence here, per CTA, took ~10 us
+            // on its own: N=2 exchange 23.4 -> 18.3 us, profiles/r2ab_exchange_fence_scope_n2.json)
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
             if (stamper) me->stamp[2] = global_ns();
             s_last = (atomicAdd(&me->done_ctas, 1u) == working - 1) ? 1 : 0;
-            asm volatile("fence.acq_rel.sys;" ::: "memory");       // the last CTA has seen every other CTA's stores
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");       // the last CTA has seen every other CTA's stores
         }
     }
     __syncthreads();
