@@ -321,7 +321,9 @@ def test_graphed_train_step_equals_eager(precision):
     assert it0 == it1 == 7
     if precision == "bf16":        # deterministic kernels: the replayed step is the eager step, bit for bit
         assert torch.equal(p0, p1) and torch.equal(m0, m1) and torch.equal(v0, v1)
-        assert l0 == l1 and abs(q0 - q1) <= 1e-5      # (the metric state is summed with float atomics across blocks)
+        # (the loss value and the metric state are sums of float atomics over the blocks of the loss kernel: equal to
+        # rounding, not bit for bit -- the gradient does not depend on them)
+        assert abs(l0 - l1) <= 1e-6 * abs(l0) and abs(q0 - q1) <= 1e-5
     else:                          # the fp32 check path accumulates weight gradients with atomics (order varies run to run)
         # (and Adam's first steps move a weight by ~lr * sign(g): a gradient at the noise level may move the other way)
         d = (p0 - p1).abs()
