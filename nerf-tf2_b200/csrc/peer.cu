@@ -9,14 +9,19 @@
 //   reduce      rank r owns slice r of the buffer: it loads that slice from every rank over NVLink (16-byte loads, all
 //               ranks' loads of an element in flight together), sums them in rank order 0..W-1
 //   broadcast   ... and stores the sum into slice r of EVERY rank's buffer, in place: slice r of any buffer is read
-//               and written by rank r only, and an element is written after it was read by the same thread
-//   barrier B   "my slice has landed everywhere" -> flags; the last CTA of the grid waits for every peer's flag, so
-//               the kernel (and with it the stream) completes only when the local buffer holds the full sum
+//               and written by rank r only, and an element is written after it was read by the same thread.
+//               With an NVSwitch multicast mapping of the block (NVLS) both steps are done by the switch:
+//               multimem.ld_reduce returns the sum over all GPUs, multimem.st replicates it into all of them
+//   barrier B   "my slice has landed everywhere": the CTAs of this GPU are ordered by a gpu-scope fence and a counter,
+//               the LAST one releases a flag to every peer at system scope (cumulative over that chain) and waits for
+//               every peer's flag, so the kernel (and with it the stream) completes only when the local buffer holds
+//               the full sum
 //
-// Every element is summed by exactly one rank in a fixed order, so all replicas receive bit-identical sums (they
-// stay bit-identical replicas) and the result does not depend on timing. Flags carry a monotonically increasing
-// epoch that lives in device memory, so a launch captured in a CUDA graph replays correctly. 4.77 MB over 8 GPUs:
-// each rank pulls 7 x 0.6 MB and pushes 7 x 0.6 MB, two flag round trips -- latency, not bandwidth.
+// Every element is summed by exactly one rank (or once by the switch) and replicated, so all replicas receive
+// bit-identical sums (they stay bit-identical replicas) and the result does not depend on timing. Flags carry a
+// monotonically increasing epoch that lives in device memory, so a launch captured in a CUDA graph replays correctly.
+// 4.77 MB over 8 GPUs is latency, not bandwidth: 25 us with NVLS, 28 us unicast, against 54 us for an NCCL all-reduce
+// (DESIGN.md 4.2c has the phase timings the kernel stamps into its header).
 //
 // Optional epilogue (adam != 0): instead of leaving after its slice, every CTA waits for barrier B and then applies
 // the fused Adam step (optim.cu) to its share of the parameters -- the exchange and the optimizer in one launch.
