@@ -6,8 +6,9 @@ is single-device; this is the new multi-GPU functionality of SUR
     views of a multi-view job), renders with replicated weights and no communication; the only
     collective is the final gather of the [n,5] (rgb, depth, acc) image rows;
   * training: the 4096-ray batch is split B/G per rank, each rank's loss is scaled by
-    1/(B_global*3) and ONE all-reduce(sum) of the flat gradient buffer precedes the fused Adam
-    step (NeRF.train_step does this when set_distributed() was called).
+    1/(B_global*3) and ONE sum of the flat gradient buffer over the ranks precedes the fused Adam
+    step (NeRF.train_step does this when set_distributed() was called: on GPUs through the library's
+    own peer-memory kernel, csrc/peer.cu, with an NCCL all-reduce as the fallback).
 
 Everything here works on any backend (NCCL on GPUs, gloo in the CPU tests).
 """

@@ -7,7 +7,7 @@ kernels behind the C ABI; torch only owns device memory, streams and the process
 
 Parameters are ONE flat fp32 device buffer (coarse model then fine model, variables in Keras
 `model.trainable_variables` order = dense_0..dense_9, rgb, sigma; kernels [in,out] row-major): the 48 `trainable_variables` are views into it, the
-gradient is one flat buffer (a single NCCL all-reduce in data-parallel training)
+gradient is one flat buffer (ONE exchange per data-parallel step, SURVEY.md 8e: the library's peer-memory kernel, or an NCCL all-reduce)
 and Adam is one fused launch.
 """
 import ctypes as C
@@ -236,7 +236,7 @@ class NeRF:
         with torch.cuda.device(self.device):
             self.flat_params = torch.from_numpy(glorot_uniform_params(seed)).to(self.device)
             # ONE flat buffer carries everything a data-parallel step exchanges: the gradient (coarse model, fine
-            # model) and, behind it, [loss, 0, 0, 0] -- one all-reduce per step
+            # model) and, behind it, [loss, 0, 0, 0] -- one exchange per step
             self._grad_buf = torch.zeros(PARAMS_TOTAL + 4, device=self.device, dtype=torch.float32)
             self.flat_grads = self._grad_buf[:PARAMS_TOTAL]
             h = C.c_void_p()
@@ -282,7 +282,7 @@ class NeRF:
         self.peer_mode = None             # "nvls" (switch reduces/replicates), "symm-p2p" or "ipc" (unicast loads/stores)
         self.peer_symmetric_memory = True   # map the blocks through torch symmetric memory (else: the library's CUDA IPC)
         self.peer_multicast = None        # NVLS multicast mapping: None = from 4 ranks up, True / False = always / never
-        self.overlap_allreduce = True     # data-parallel: all-reduce the coarse gradient while the fine backward runs
+        self.overlap_allreduce = True     # NCCL path: all-reduce the coarse gradient while the fine backward runs
         self.graph_overlap_allreduce = True   # the same fork/join inside a captured step
         self.fused_forward = True         # forward()/predict()/render: the whole march as one C-ABI call (nerfb200_forward)
         self.use_cuda_graph = bool(int(cuda_graph))     # train_step as one CUDA graph per batch shape (after two eager steps)
