@@ -10,6 +10,8 @@ PARITY UNPINNED for this file: the arithmetic lives in tensorflow==2.6.0 /
 keras==2.7.0 (requirements.txt:44,17), which cannot be installed here, and the
 reference ships no golden vectors. Keras Dense = act(x @ kernel[in,out] + bias);
 Keras Adam (OptimizerV2, non-amsgrad, epsilon=1e-7) as in SURVEY.md Appendix A.
+Cross-checked (not pinned) against independent implementations of the same published semantics:
+tests/test_oracle_crosscheck.py (scikit-learn's Adam and MLP forward, torch linear, fp64 finite differences).
 """
 import math
 
@@ -24,7 +26,8 @@ LAYER_NAMES = [f"dense_{i}" for i in range(10)] + ["rgb", "sigma"]
 # Order of Keras' `model.layers` (hence trainable_variables / get_weights / optimizer slots) for the
 # functional model of core/model.py:334-394: Functional._map_graph_network sorts layers by decreasing
 # depth from the outputs [rgb, sigma] and breaks ties by the output-first traversal index, so the two
-# heads come last, rgb before sigma. (TensorFlow is not installable here: restated, not executed.)
+# heads come last, rgb before sigma. (TensorFlow is not installable here: restated, not executed;
+# tests/test_keras_layer_order.py runs the restated algorithm on the reference's graph.)
 # (fan_in, fan_out) per layer (core/model.py:366-387)
 LAYER_SHAPES = {
     "dense_0": (63, 256), "dense_1": (256, 256), "dense_2": (256, 256), "dense_3": (256, 256),
