@@ -215,6 +215,7 @@ struct nerfb200_peer {
     int world = 0, rank = 0, device = 0, connected = 0;
     int timeout_s = 120;              // how long a rank waits for its peers inside the kernel before it traps
     int owned = 1;                    // the blocks were allocated / mapped by this library (CUDA IPC)
+    int occupancy = 0;                // resident CTAs of the exchange kernel per SM (queried at the first launch)
     int64_t n = 0;
     uint8_t* base[kPeerMaxWorld] = {};
     uint8_t* mc = nullptr;
@@ -327,10 +328,12 @@ static int peer_launch(nerfb200_peer* peer, const AdamArgs* ad, void* stream) {
     const int64_t per = (P.n4 + P.world - 1) / P.world;
     const int64_t units = (ad && ad->n / 4 > per) ? ad->n / 4 : per;       // 16-byte units of the widest phase
     // every CTA of the grid must be resident at once: with the Adam epilogue all of them wait for the peers' flags
-    int occ = 1;
-    NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peer_allreduce_kernel, kPeerThreads, 0));
-    if (occ > 4) occ = 4;
-    if (occ < 1) occ = 1;
+    if (peer->occupancy <= 0) {         // once per handle
+        int occ = 1;
+        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, peer_allreduce_kernel, kPeerThreads, 0));
+        peer->occupancy = occ > 4 ? 4 : (occ < 1 ? 1 : occ);
+    }
+    const int occ = peer->occupancy;
     int64_t grid = (units + kPeerThreads - 1) / kPeerThreads;
     if (grid > (int64_t)num_sms() * occ) grid = (int64_t)num_sms() * occ;
     if (grid < 1) grid = 1;
@@ -344,7 +347,8 @@ int nerfb200_peer_allreduce(nerfb200_peer* peer, void* stream) { return peer_lau
 int nerfb200_peer_allreduce_adam(nerfb200_peer* peer, int64_t n, float* params, float* m, float* v, int64_t iterations,
                                  const int64_t* step_state, void* stream) {
     NB_CHECK_ARG(peer && params && m && v && iterations >= 0, "peer_allreduce_adam: bad arguments");
-    NB_CHECK_ARG(n > 0 && n <= peer->n, "peer_allreduce_adam: n must be in (0, exchanged floats]");
+    NB_CHECK_ARG(n > 0 && n <= peer->n && n % 4 == 0, "peer_allreduce_adam: n must be a multiple of 4 in (0, exchanged floats]");
+    NB_CHECK_ARG((((uintptr_t)params | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "peer_allreduce_adam: params, m and v must be 16-byte aligned");
     AdamArgs ad;
     ad.p = params; ad.m = m; ad.v = v; ad.step_dev = step_state; ad.n = n;
     ad.lr_t = adam_lr_t(iterations);

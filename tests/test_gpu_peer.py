@@ -88,6 +88,9 @@ def test_exchange_refuses_to_launch_unconnected_or_misused():
     assert lib.nerfb200_peer_allreduce(h, _lib.stream_ptr()) == 10003 and b"peer_connect" in lib.nerfb200_last_error()
     x = torch.zeros(2048, device="cuda")
     assert lib.nerfb200_peer_allreduce_adam(h, 2048, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), 0, None, _lib.stream_ptr()) == 10001
+    assert lib.nerfb200_peer_allreduce_adam(h, 1022, _lib.ptr(x), _lib.ptr(x), _lib.ptr(x), 0, None, _lib.stream_ptr()) == 10001   # 4 | n
+    assert lib.nerfb200_peer_allreduce_adam(h, 1024, C.c_void_p(x.data_ptr() + 4), _lib.ptr(x), _lib.ptr(x), 0, None,
+                                            _lib.stream_ptr()) == 10001 and b"aligned" in lib.nerfb200_last_error()
     hd = C.create_string_buffer(64)
     _lib.check(lib.nerfb200_peer_handle(h, hd), "peer_handle")
     assert any(hd.raw)                                              # an IPC handle was produced
