@@ -191,6 +191,16 @@ NERFB200_API int nerfb200_composite_bwd(int64_t B, int S, const float* sigma, co
                            const float* t_vals, int white_bg, const float* d_pred_rgb,
                            float* d_sigma, float* d_rgb, void* stream);
 
+/* Training form (NeRF.train_step, core/model.py:148-170): nerfb200_composite_fwd, the loss of
+ * nerfb200_mse_loss_grad on this output (loss += mean((pred-gt)^2) with the mean over B_global*3 values; metric[0] +=
+ * sum((gt-pred)^2), metric[1] += B when metric != NULL) and nerfb200_composite_bwd with d_pred = 2*(pred-gt)/(B_global*3),
+ * as ONE launch over values that stay in registers. Same arithmetic as the three separate calls (the loss is summed per
+ * ray instead of per 256 values). weights and metric may be NULL. */
+NERFB200_API int nerfb200_composite_train(int64_t B, int S, const float* sigma, const float* rgb, const float* t_vals,
+                           int white_bg, const float* rgb_gt, int64_t B_global, float* weights, float* pred_rgb,
+                           float* pred_depth, float* acc_map, float* d_sigma, float* d_rgb, float* loss, float* metric,
+                           void* stream);
+
 /* ---- a10: hierarchical (inverse-transform) sampler ----------------------------------------
  * create_input_batch_fine_model (utils/ray_utils.py:276-406): pdf/cdf from (w+1e-5), upper-bound
  * searchsorted over the Nc-1 inner CDF edges, inversion with the pdf<1e-8 mask, then

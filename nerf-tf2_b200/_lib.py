@@ -49,6 +49,7 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_composite_fwd": (_i32, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_composite_bwd": (_i32, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "nerfb200_composite_train": (_i32, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_sample_fine": (_i32, [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _u64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_mse_loss_grad": (_i32, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nerfb200_adam_step": (_i32, [_i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -518,13 +518,19 @@ class NeRF:
             st_c = self._scratch("stash_c", load().nerfb200_mlp_stash_bytes(R_c, precision))
             st_f = self._scratch("stash_f", load().nerfb200_mlp_stash_bytes(R_f, precision))
         rgb_c, sig_c = self._mlp(COARSE, rays_o, rays_d, t_c, precision, st_c)
-        pp_c = ray_utils.post_process_model_output(rgb_c, sig_c, t_c, self.white_bg)
+        if _train is not None:
+            # training: integrator + loss term + integrator backward of each model as ONE launch (nerfb200_composite_train)
+            pp_c, ds_c, dr_c = ray_utils.composite_train(rgb_c, sig_c, t_c, self.white_bg, _train["gt"], _train["Bg"], _train["loss"])
+        else:
+            pp_c = ray_utils.post_process_model_output(rgb_c, sig_c, t_c, self.white_bg)
         t_f = ray_utils.sample_fine(s.N_fine, pp_c["weights"], edges, t_c, u_fine, seed, ray0, step_state=_step_state)
         rgb_f, sig_f = self._mlp(FINE, rays_o, rays_d, t_f, precision, st_f)
-        pp_f = ray_utils.post_process_model_output(rgb_f, sig_f, t_f, self.white_bg, need_weights=need_weights)
         if _train is not None:
-            _train.update(dict(t_c=t_c, t_f=t_f, rgb_c=rgb_c, sig_c=sig_c, rgb_f=rgb_f, sig_f=sig_f,
-                               st_c=st_c, st_f=st_f))
+            pp_f, ds_f, dr_f = ray_utils.composite_train(rgb_f, sig_f, t_f, self.white_bg, _train["gt"], _train["Bg"], _train["loss"],
+                                                         metric_state=_train["metric"], need_weights=False)
+            _train.update(dict(t_c=t_c, t_f=t_f, st_c=st_c, st_f=st_f, ds_c=ds_c, dr_c=dr_c, ds_f=ds_f, dr_f=dr_f))
+        else:
+            pp_f = ray_utils.post_process_model_output(rgb_f, sig_f, t_f, self.white_bg, need_weights=need_weights)
         return pp_c, pp_f
 
     def _forward_one_call(self, rays_o, rays_d, near, far, u_coarse, u_fine, seed, step_state, ray0, precision, need_weights):
@@ -573,29 +579,23 @@ class NeRF:
         prec = self.train_precision
         B = rays_o.shape[0]
         Bg = B * self.world_size if global_batch is None else global_batch
-        tr = {}
-        pp_c, pp_f = self.forward(rays_o, rays_d, near, far, u_coarse, u_fine, ray0, precision=prec, _train=tr,
-                                  _step_state=step_state)
         self._grad_buf.zero_()                       # the kernels accumulate into the gradient and the loss
         loss = self._grad_buf[PARAMS_TOTAL:PARAMS_TOTAL + 1]
-        d_c = torch.empty((B, 3), device=self.device, dtype=torch.float32)
-        d_f = torch.empty((B, 3), device=self.device, dtype=torch.float32)
         metric = self.metrics[0] if self.metrics else None
         if metric is not None:
             metric._ensure(self.device)
+        # the forward's integrators also add the two MeanSquaredError terms to `loss` (and the fine one to the metric
+        # state) and leave d(loss)/d(sigma, rgb) of both models in `tr` (ray_utils.composite_train)
+        tr = {"gt": rgb.contiguous(), "Bg": Bg, "loss": loss, "metric": metric.state if metric is not None else None}
+        pp_c, pp_f = self.forward(rays_o, rays_d, near, far, u_coarse, u_fine, ray0, precision=prec, _train=tr,
+                                  _step_state=step_state)
         lib = load()
-        check(lib.nerfb200_mse_loss_grad(B, Bg, ptr(pp_c["pred_rgb"]), ptr(rgb), ptr(d_c), ptr(loss),
-                                         C.c_void_p(0), stream_ptr()), "mse_loss_grad")
-        check(lib.nerfb200_mse_loss_grad(B, Bg, ptr(pp_f["pred_rgb"]), ptr(rgb), ptr(d_f), ptr(loss),
-                                         ptr(metric.state) if metric is not None else C.c_void_p(0),
-                                         stream_ptr()), "mse_loss_grad")
-        ds_c, dr_c = ray_utils.composite_backward(tr["rgb_c"], tr["sig_c"], tr["t_c"], self.white_bg, d_c)
+        ds_c, dr_c, ds_f, dr_f = tr["ds_c"], tr["dr_c"], tr["ds_f"], tr["dr_f"]
         n_dw = self._dw_overlap_sms if prec != FP32 else 0
         if n_dw <= 0:
             self._mlp_backward(COARSE, rays_o, rays_d, tr["t_c"], dr_c, ds_c, prec, tr["st_c"])
             if coarse_done is not None:
                 coarse_done()                        # data-parallel: the coarse half of the gradient is final
-            ds_f, dr_f = ray_utils.composite_backward(tr["rgb_f"], tr["sig_f"], tr["t_f"], self.white_bg, d_f)
             self._mlp_backward(FINE, rays_o, rays_d, tr["t_f"], dr_f, ds_f, prec, tr["st_f"])
             return loss, pp_c, pp_f
         # Phase-split backward. Per model: backward-data (writes the gradient stash: HBM-write bound), then the
@@ -614,7 +614,6 @@ class NeRF:
                                              ptr(ws_c, u8), ptr(tr["st_c"], u8), 0, stream_ptr()), "mlp_backward_data")
         ev = torch.cuda.Event()
         ev.record(main)
-        ds_f, dr_f = ray_utils.composite_backward(tr["rgb_f"], tr["sig_f"], tr["t_f"], self.white_bg, d_f)
         check(lib.nerfb200_mlp_backward_data(self._ctx, FINE, Bf, Sf, ptr(self.flat_params), ptr(dr_f), ptr(ds_f), prec,
                                              ptr(ws_f, u8), ptr(tr["st_f"], u8), self._num_sms - n_dw, stream_ptr()),
               "mlp_backward_data")

@@ -194,6 +194,29 @@ def sigma_to_alpha(sigma, diffs):
     return 1 - torch.exp(-sigma * diffs)
 
 
+def composite_train(sample_rgb, sigma, t_vals, white_bg, rgb_gt, B_global, loss, metric_state=None, need_weights=True):
+    """The integrator of a training step in ONE launch (nerfb200_composite_train): post_process_model_output, the
+    MeanSquaredError term of this output added to `loss` (and the PSNRMetric state to `metric_state`), and the gradient
+    w.r.t. (sigma, sample_rgb). Returns (post_proc dict, d_sigma [B*S], d_rgb [B*S,3])."""
+    B, S = t_vals.shape
+    dev = t_vals.device
+    weights = torch.empty((B, S), device=dev, dtype=torch.float32) if need_weights else None
+    pred_rgb = torch.empty((B, 3), device=dev, dtype=torch.float32)
+    pred_depth = torch.empty((B,), device=dev, dtype=torch.float32)
+    acc_map = torch.empty((B,), device=dev, dtype=torch.float32)
+    d_sigma = torch.empty((B * S,), device=dev, dtype=torch.float32)
+    d_rgb = torch.empty((B * S, 3), device=dev, dtype=torch.float32)
+    check(load().nerfb200_composite_train(B, S, ptr(sigma.reshape(-1)), ptr(sample_rgb), ptr(t_vals.contiguous()),
+                                          int(bool(white_bg)), ptr(rgb_gt.contiguous()), int(B_global),
+                                          ptr(weights, allow_none=True), ptr(pred_rgb), ptr(pred_depth), ptr(acc_map),
+                                          ptr(d_sigma), ptr(d_rgb), ptr(loss), ptr(metric_state, allow_none=True),
+                                          stream_ptr()), "composite_train")
+    out = {"acc_map": acc_map, "pred_rgb": pred_rgb, "pred_depth": pred_depth}
+    if need_weights:
+        out["weights"] = weights
+    return out, d_sigma, d_rgb
+
+
 def composite_backward(sample_rgb, sigma, t_vals, white_bg, d_pred_rgb):
     """Gradient of post_process_model_output's pred_rgb w.r.t. (sigma, sample_rgb)."""
     B, S = t_vals.shape

@@ -129,6 +129,70 @@ def test_integrator_backward_matches_autograd():
         assert np.allclose(host(dr), rt.grad.numpy(), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("S", [64, 192, 384, 100, 33, 2])
+@pytest.mark.parametrize("white_bg", [True, False])
+def test_training_integrator_equals_forward_loss_backward_launches(S, white_bg):
+    """nerfb200_composite_train (integrator + MeanSquaredError term + integrator backward as ONE launch, NeRF.train_step,
+    core/model.py:148-170) against the three launches it replaces: forward outputs BIT-IDENTICAL to
+    nerfb200_composite_fwd (same lane mapping and operations, so a training forward resamples exactly like a render
+    forward), gradients equal to nerfb200_composite_bwd fed with nerfb200_mse_loss_grad's d_pred up to fp32 summation
+    order, loss and metric state equal to rounding; odd ray counts (the two-rays-per-warp form of S = 64 with a last
+    half-empty warp), rows that are not 16-byte aligned, accumulation into a non-zero loss."""
+    from nerf_tf2_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(S)
+    for B, Bg in ((37, 37), (256, 1024), (1, 1)):
+        t = np.sort(rng.random((B, S), dtype=F32) * F32(0.8) + F32(0.4), axis=1)
+        sig = (rng.random((B * S,), dtype=F32) * 15 * (rng.random((B * S,)) > 0.4)).astype(F32)
+        rgb = rng.random((B * S, 3), dtype=F32)
+        gt = rng.random((B, 3), dtype=F32)
+        dt, dsg, drgb, dgt = dev(t), dev(sig), dev(rgb), dev(gt)
+        # the three launches
+        pp = ru.post_process_model_output(drgb, dsg, dt, white_bg)
+        d_pred = torch.empty((B, 3), device="cuda"); loss0 = torch.full((1,), 0.25, device="cuda"); met0 = torch.zeros(2, device="cuda")
+        _lib.check(lib.nerfb200_mse_loss_grad(B, Bg, _lib.ptr(pp["pred_rgb"]), _lib.ptr(dgt), _lib.ptr(d_pred), _lib.ptr(loss0),
+                                              _lib.ptr(met0), _lib.stream_ptr()), "mse_loss_grad")
+        ds0, dr0 = ru.composite_backward(drgb, dsg, dt, white_bg, d_pred)
+        # the one launch
+        loss1 = torch.full((1,), 0.25, device="cuda"); met1 = torch.zeros(2, device="cuda")
+        pp1, ds1, dr1 = ru.composite_train(drgb, dsg, dt, white_bg, dgt, Bg, loss1, metric_state=met1)
+        for k in ("pred_rgb", "pred_depth", "acc_map", "weights"):
+            assert torch.equal(pp[k], pp1[k]), (S, B, k)
+        assert abs(float(loss1) - float(loss0)) <= 2e-6 * abs(float(loss0))
+        assert abs(float(met1[0]) - float(met0[0])) <= 2e-6 * max(1.0, float(met0[0])) and float(met1[1]) == float(met0[1]) == B
+        m = torch.ones((B, S), dtype=torch.bool, device="cuda"); m[:, -1] = False       # delta_last = 1e10 amplifies rounding
+        scale = float(ds0.reshape(B, S)[m].abs().max())
+        assert float((ds1.reshape(B, S) - ds0.reshape(B, S))[m].abs().max()) <= 2e-5 * max(scale, 1e-30), (S, B)
+        last0, last1 = ds0.reshape(B, S)[:, -1], ds1.reshape(B, S)[:, -1]
+        assert torch.allclose(last1, last0, rtol=1e-3, atol=1e-3 * float(last0.abs().max()) + 1e-30)
+        assert torch.allclose(dr1, dr0, rtol=1e-6, atol=1e-9)
+        # without the optional outputs; the same forward results
+        loss2 = torch.zeros(1, device="cuda")
+        pp2, ds2, dr2 = ru.composite_train(drgb, dsg, dt, white_bg, dgt, Bg, loss2, need_weights=False)
+        assert "weights" not in pp2 and torch.equal(pp2["pred_rgb"], pp["pred_rgb"]) and torch.equal(ds2, ds1) and torch.equal(dr2, dr1)
+    # rows that are not 16-byte aligned take the scalar staging path: identical results
+    B = 9
+    t = np.sort(rng.random((B, S), dtype=F32), axis=1); sig = rng.random((B * S,), dtype=F32); rgb = rng.random((B * S, 3), dtype=F32)
+    gt = dev(rng.random((B, 3), dtype=F32))
+    pad = lambda a: torch.cat([torch.zeros(1, device="cuda"), dev(a).reshape(-1)])[1:].reshape(a.shape)      # 4-byte offset view
+    la, lb = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    pa, dsa, dra = ru.composite_train(dev(rgb), dev(sig), dev(t), white_bg, gt, B, la)
+    tt, ss, rr = pad(t), pad(sig), pad(rgb)
+    assert tt.data_ptr() % 16 != 0
+    out = {k: torch.empty_like(v) for k, v in pa.items()}
+    dsb, drb = torch.empty_like(dsa), torch.empty_like(dra)
+    _lib.check(lib.nerfb200_composite_train(B, S, ss.data_ptr(), rr.data_ptr(), tt.data_ptr(), int(white_bg), _lib.ptr(gt), B,
+                                            _lib.ptr(out["weights"]), _lib.ptr(out["pred_rgb"]), _lib.ptr(out["pred_depth"]),
+                                            _lib.ptr(out["acc_map"]), _lib.ptr(dsb), _lib.ptr(drb), _lib.ptr(lb), None,
+                                            _lib.stream_ptr()), "composite_train")
+    for k in pa:
+        assert torch.equal(pa[k], out[k]), k
+    assert torch.equal(dsa, dsb) and torch.equal(dra, drb) and abs(float(la) - float(lb)) <= 1e-6 * abs(float(la))   # (float atomics)
+    # argument validation
+    assert lib.nerfb200_composite_train(4, 1, None, None, None, 0, None, 4, None, None, None, None, None, None, None, None, None) == 10001
+    assert lib.nerfb200_composite_train(4, 64, 1, 1, 1, 0, 1, 2, None, 1, 1, 1, 1, 1, 1, None, None) == 10001     # B_global < B
+
+
 @pytest.mark.parametrize("tag", ["inv", "lin"])
 def test_fine_sampler_vs_reference_fixture(golden, tag):
     g = golden["ref_sampling_composite"]
