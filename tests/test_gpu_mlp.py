@@ -227,7 +227,7 @@ def test_overlapped_backward_equals_sequential_backward(golden, n_dw):
         torch.cuda.synchronize()
         grads.append((float(loss.item()), nerf.flat_grads.double().clone()))
     (l0, a), (l1, b) = grads
-    assert l0 == l1
+    assert abs(l0 - l1) <= 1e-6 * abs(l0)          # (the loss is a sum of per-ray float atomics: equal to rounding)
     scale = float(a.abs().max())
     assert float((a - b).abs().max()) <= 2e-5 * scale
     assert float(torch.nn.functional.cosine_similarity(a, b, dim=0)) >= 1 - 1e-9
