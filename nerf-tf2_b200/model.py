@@ -676,7 +676,7 @@ class NeRF:
     @_on_device
     def _train_step_graphed(self, ro, rd, near, far, rgb, ray0):
         """The whole step -- sampling, both forwards, loss, both backwards, the gradient all-reduce, Adam, the repack of
-        the operand images -- as ONE CUDA graph per batch shape: ~35 launches per step are otherwise issued one by
+        the operand images -- as ONE CUDA graph per batch shape: ~30 launches per step are otherwise issued one by
         one from Python, which is what bounds a data-parallel step of 512 rays per GPU. The first two steps of a
         shape run eagerly (they size every scratch buffer), the third is captured, later ones replay it. What changes
         from step to step lives on the device: the input batch (copied into static buffers), the sampling step and
