@@ -165,3 +165,21 @@ def test_bench_reads_traffic_from_the_committed_ncu_exports():
     assert 3e7 < th < 1.2e8
     assert bench.ncu_traffic("no_such_file.csv", "x") == (None, None)
     assert bench.ncu_traffic(bench.NCU_HBM_CSV, "no_such_kernel") == (None, None)
+
+
+def test_documents_only_cite_files_that_exist():
+    """DESIGN.md / README.md / INTEGRATION.md / tools/README.md cite measurements and sources by path: every cited path
+    under profiles/, tools/, tests/, oracle/, include/ and the package must exist in the tree."""
+    import os
+    import re
+    from conftest import ROOT
+    missing = []
+    for doc in ("DESIGN.md", "README.md", "INTEGRATION.md", os.path.join("tools", "README.md")):
+        txt = open(os.path.join(ROOT, doc)).read()
+        for m in re.findall(r"((?:profiles|tools|tests|oracle|include|nerf-tf2_b200)/[A-Za-z0-9_\-./*{},<>…]+)", txt):
+            m = m.rstrip(".,)`:;")
+            if any(c in m for c in "*{}<>…") or m == "oracle/_ref":      # patterns; the directory that by design does not exist
+                continue
+            if not os.path.exists(os.path.join(ROOT, m)):
+                missing.append((doc, m))
+    assert not missing, missing
